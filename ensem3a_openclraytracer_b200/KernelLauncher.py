@@ -1,0 +1,82 @@
+"""Drop-in replacement for the reference's KernelLauncher.py (PyOpenCL) on B200.
+
+Same class name, same three method signatures in the same positional order
+(reference KernelLauncher.py:8, :33, :90), same in-place / synchronous behaviour:
+`launch_Raytracing` fills the caller's `h_img_out` and returns None when the image is on the host
+(the reference's blocking enqueue_copy, :78); `launch_ImgProcessing` fills `h_out`.  main.py and
+UI.py therefore drive it unchanged (main.py:28,84-86).
+
+The work is done by the CUDA kernels behind the C ABI of include/b200rt.h; there is no OpenCL,
+CPU or PyTorch fallback: constructing a KernelLauncher without a usable B200 raises.
+
+Differences a caller can observe (all documented in INTEGRATION.md):
+  * the OpenCL objects passed to __init__ are accepted and ignored;
+  * geometry / environment uploads are cached by content between calls (the UI re-creates
+    identical arrays for every render, UI.py:98), materials are always refreshed;
+  * non-square frames: width = int(cam[6]), height = imgDim // width, exactly what the reference
+    kernel computes for such a launch (Raytracing.cl:21-29);
+  * extra behaviour is opt-in through attributes (`rng_mode`, `traversal`, `seed`, ...) that the
+    reference's callers never touch, so the default is the reference's result.
+"""
+import numpy as np
+
+from . import _capi
+
+
+class KernelLauncher(object):
+
+    def __init__(self, context=None, platform=None, device=None, queue=None, cuda_device=0):
+        self.platform = platform
+        self.device = device
+        self.context = context
+        self.queue = queue
+        self._ctx = _capi.Context(cuda_device)
+        # opt-in knobs; defaults reproduce the reference
+        self.rng_mode = _capi.RNG_REFERENCE
+        self.traversal = _capi.TRAVERSAL_FAST
+        self.seed = 0
+        self.stack_cap = 20
+        self.collect_stats = False
+        self.last_stats = None
+
+    # reference KernelLauncher.py:33
+    def launch_Raytracing(self, h_img_out, h_vertex_p, h_vertex_n, h_vertex_uv, h_face_data, h_material_data,
+                          h_light_data, h_BVH, h_cam, h_envData, imgDim, spp, maxBounce, h_IBL):
+        cam = np.ascontiguousarray(h_cam, dtype=np.float32).reshape(-1)
+        if cam.size < 10:
+            raise ValueError("h_cam must hold 10 floats (main.py:59-61)")
+        width = int(cam[6])
+        imgDim = int(imgDim)
+        if width <= 0 or imgDim <= 0 or imgDim % width:
+            raise ValueError(f"imgDim={imgDim} is not a whole number of rows of cam[6]={width} pixels")
+        height = imgDim // width
+        if not isinstance(h_img_out, np.ndarray) or h_img_out.dtype != np.float32 or not h_img_out.flags["C_CONTIGUOUS"]:
+            raise TypeError("h_img_out must be a C-contiguous float32 numpy array (it is filled in place)")
+        if h_img_out.size < imgDim * 3:
+            raise ValueError(f"h_img_out has {h_img_out.size} elements, needs {imgDim * 3}")
+
+        self._ctx.set_scene(h_vertex_p, h_vertex_n, h_vertex_uv, h_face_data, h_material_data, h_light_data, h_BVH)
+        # h_IBL is a PIL RGBA image in the reference (uses .size and .tobytes(), KernelLauncher.py:72);
+        # an (H, W, 4) uint8 array is accepted as well
+        if hasattr(h_IBL, "tobytes") and hasattr(h_IBL, "size") and not isinstance(h_IBL, np.ndarray):
+            w, h = h_IBL.size
+            self._ctx.set_ibl(h_IBL.tobytes(), w, h)
+        else:
+            self._ctx.set_ibl(np.asarray(h_IBL))
+
+        opts = _capi.make_opts(rng_mode=self.rng_mode, traversal=self.traversal, stack_cap=self.stack_cap,
+                               seed=self.seed, collect_stats=self.collect_stats)
+        out = h_img_out.reshape(-1)[:imgDim * 3]
+        self._ctx.render(cam[:10], h_envData, width, height, int(spp), int(maxBounce), out=out, opts=opts)
+        self.last_stats = self._ctx.stats()
+
+    # reference KernelLauncher.py:90
+    def launch_ImgProcessing(self, h_src, h_out, SIZE):
+        src = np.ascontiguousarray(h_src, dtype=np.float32)
+        if not isinstance(h_out, np.ndarray) or h_out.dtype != np.float32 or not h_out.flags["C_CONTIGUOUS"]:
+            raise TypeError("h_out must be a C-contiguous float32 numpy array (it is filled in place)")
+        # global size = h_src.shape, N = SIZE*SIZE*3 (KernelLauncher.py:101-102)
+        self._ctx.img_processing(src.reshape(-1), h_out.reshape(-1), int(SIZE) * int(SIZE) * 3, src.size)
+
+    def close(self):
+        self._ctx.close()

@@ -1,0 +1,926 @@
+// b200rt — host side of the C ABI declared in include/b200rt.h.
+//
+// Owns the CUDA context objects of one GPU, validates and repacks the reference-layout scene
+// buffers into the float4 layouts rt_trace.cuh consumes, evaluates the per-frame
+// constants, and launches the kernels of rt_kernels.cuh.  No CPU rendering path exists here: every
+// entry point that produces pixels, hits or tonemapped values does so by launching a kernel.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/b200rt.h"
+#include "rt_kernels.cuh"
+
+using namespace b200rt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct b200rt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  std::string err;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+
+  // scene
+  bool have_scene = false;
+  uint64_t scene_hash = 0, mat_hash = 0;
+  DevBuf d_nodes, d_tris, d_normals, d_mats, d_bvh9;
+  int n_nodes9 = 0, n_inner = 0, n_tris = 0, n_mats = 0;
+  int depth = 0, ref_stack_need = 0;
+  bool canonical = true;
+  int root_ref = 0;
+  float root_box[6] = {0, 0, 0, 0, 0, 0};
+  float cull_abs = 0.0f;
+  int fast_div_ok = 1;
+  std::vector<int32_t> tri_mat;  // for re-validating material edits
+
+  // environment map
+  bool have_ibl = false;
+  uint64_t ibl_hash = 0;
+  cudaArray_t ibl_array = nullptr;
+  cudaTextureObject_t ibl_tex = 0;
+  int ibl_w = 0, ibl_h = 0;
+
+  // per-frame
+  DevBuf d_prim_dirk, d_prim_tri, d_out, d_misc, d_tmp_a, d_tmp_b;
+  DeviceCounters *d_counters = nullptr;
+  unsigned int *d_work = nullptr;
+
+  b200rt_stats stats;
+  bool stats_pending = false;  // async render enqueued; counters/events not read yet
+};
+
+namespace {
+
+int fail(b200rt_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(c, B200RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+int ensure(b200rt_ctx *c, DevBuf &b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.cap >= bytes) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  CU(cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  return 0;
+}
+
+uint64_t hash_bytes(const void *p, size_t n, uint64_t h) {
+  const unsigned char *b = static_cast<const unsigned char *>(p);
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    memcpy(&w, b + i, 8);
+    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+  }
+  for (; i < n; ++i) h = (h ^ b[i]) * 0x100000001B3ull;
+  return h ^ (uint64_t)n;
+}
+
+// correctly-rounded binary32 cos/sin/tan on the host: binary64 libm, one rounding (rt_math.cuh contract)
+float h_cos(float a) { return (float)std::cos((double)a); }
+float h_sin(float a) { return (float)std::sin((double)a); }
+float h_tan(float a) { return (float)std::tan((double)a); }
+
+rotor h_rotor(float angle, v3 axis) {
+  float half = angle * 0.5f;
+  return make_rotor(h_cos(half), h_sin(half), axis);
+}
+
+const float kDeg2Rad = 3.14f / 180.0f;
+
+// Per-frame constants.  Raytracing.cl:24,27,33-35,115-118 and MathLib.cl:73-74.
+void frame_setup(const b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp,
+                 int max_bounce, const b200rt_opts &o, FrameParams *F) {
+  F->width = width;
+  F->height = height;
+  F->cam_pos = mk3(cam[0], cam[1], cam[2]);
+  F->focal_off = 1.0f / (2.0f * h_tan(cam[9] / 2.0f));
+  F->step = (float)(1.0 / (double)cam[6]);
+  F->cam_rx = h_rotor(cam[3] * kDeg2Rad, mk3(1, 0, 0));
+  F->cam_ry = h_rotor(cam[4] * kDeg2Rad, mk3(0, 1, 0));
+  F->cam_rz = h_rotor(cam[5] * kDeg2Rad, mk3(0, 0, 1));
+  v3 s = mk3(1, 1, 1);
+  if (env) {
+    s = apply_rotor(h_rotor(env[0] * kDeg2Rad, mk3(1, 0, 0)), s);
+    s = apply_rotor(h_rotor(env[1] * kDeg2Rad, mk3(0, 1, 0)), s);
+    s = apply_rotor(h_rotor(env[2] * kDeg2Rad, mk3(0, 0, 1)), s);
+  }
+  F->sun_dir = s;
+  F->sun_power = env ? env[3] : 0.0f;
+  F->ibl_power = env ? env[4] : 0.0f;
+  F->ibl_r1 = h_rotor(90 * kDeg2Rad, mk3(1, 0, 0));
+  F->ibl_r2 = h_rotor(90 * kDeg2Rad, mk3(0, 1, 0));
+  F->ibl_w = c->ibl_w;
+  F->ibl_h = c->ibl_h;
+  F->spp = spp;
+  F->max_bounce = max_bounce;
+  F->s0 = o.sample_begin;
+  F->s1 = o.sample_end;
+  if (F->s1 <= 0) { F->s0 = 0; F->s1 = spp; }
+  F->pixel_begin = o.pixel_begin;
+  F->pixel_end = o.pixel_end;
+  if (F->pixel_end <= 0) { F->pixel_begin = 0; F->pixel_end = width * height; }
+  F->out_mode = o.output;
+  F->rng_mode = o.rng_mode;
+  F->key0 = (uint32_t)(o.seed & 0xffffffffull);
+  F->key1 = (uint32_t)(o.seed >> 32);
+}
+
+bool use_smem_scene(const b200rt_ctx *c) {
+  size_t bytes = (size_t)c->n_inner * 64 + (size_t)c->n_tris * 64;
+  return bytes <= 64 * 1024;
+}
+
+size_t stack_bytes(const b200rt_ctx *c) { return (size_t)kBlock * (size_t)(c->depth + 2) * sizeof(float2); }
+
+size_t smem_bytes(const b200rt_ctx *c, bool smem_scene) {
+  size_t b = stack_bytes(c);
+  if (smem_scene) b += (size_t)c->n_inner * 64 + (size_t)c->n_tris * 64;
+  return b;
+}
+
+void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float *d_out, KernelArgs *A) {
+  A->F = F;
+  SceneView &S = A->S;
+  S.nodes = static_cast<const float4 *>(c->d_nodes.p);
+  S.tris = static_cast<const float4 *>(c->d_tris.p);
+  S.normals = static_cast<const float4 *>(c->d_normals.p);
+  S.mats = static_cast<const float *>(c->d_mats.p);
+  S.bvh9 = static_cast<const float *>(c->d_bvh9.p);
+  S.root_ref = c->root_ref;
+  for (int i = 0; i < 6; ++i) S.root_box[i] = c->root_box[i];
+  S.cull_abs = c->cull_abs;
+  int cap = o.stack_cap <= 0 ? 20 : (o.stack_cap > 64 ? 64 : o.stack_cap);
+  S.stack_cap = cap;
+  S.fast_div_ok = c->fast_div_ok;
+  A->ibl = c->ibl_tex;
+  A->prim_dirk = static_cast<float4 *>(c->d_prim_dirk.p);
+  A->prim_tri = static_cast<int *>(c->d_prim_tri.p);
+  A->out = d_out;
+  A->work_counter = c->d_work;
+  A->counters = c->d_counters;
+  A->n_nodes = c->n_inner;
+  A->n_tris = c->n_tris;
+  A->stack_depth = c->depth + 2;
+  A->tiles_x = (F.width + 7) / 8;
+  int tiles_y = (F.height + 3) / 4;
+  A->n_work = A->tiles_x * tiles_y * 32;
+}
+
+int effective_traversal(const b200rt_ctx *c, const b200rt_opts &o) {
+  if (!c->canonical) return B200RT_TRAVERSAL_REFERENCE;  // the fast path needs a strict two-child tree
+  return o.traversal;
+}
+
+template <typename K>
+int set_smem_attr(b200rt_ctx *c, K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <typename K>
+int persistent_grid(b200rt_ctx *c, K kernel, size_t smem, int *grid) {
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
+  if (per_sm < 1) return fail(c, B200RT_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+  *grid = per_sm * c->sm_count;
+  return 0;
+}
+
+template <int TRAV, bool SMEM>
+int launch_primary_t(b200rt_ctx *c, const KernelArgs &A, bool parity, int *tri_out, float *k_out) {
+  size_t smem = smem_bytes(c, SMEM);
+  int grid = 0;
+  if (parity) {
+    auto k = k_primary<TRAV, SMEM, true>;
+    if (set_smem_attr(c, k, smem)) return B200RT_ERR_CUDA;
+    if (persistent_grid(c, k, smem, &grid)) return B200RT_ERR_CUDA;
+    int need = (A.n_work + kBlock - 1) / kBlock;
+    if (grid > need) grid = need;
+    k<<<grid, kBlock, smem, c->stream>>>(A, tri_out, k_out);
+  } else {
+    auto k = k_primary<TRAV, SMEM, false>;
+    if (set_smem_attr(c, k, smem)) return B200RT_ERR_CUDA;
+    if (persistent_grid(c, k, smem, &grid)) return B200RT_ERR_CUDA;
+    int need = (A.n_work + kBlock - 1) / kBlock;
+    if (grid > need) grid = need;
+    k<<<grid, kBlock, smem, c->stream>>>(A, tri_out, k_out);
+  }
+  CU(cudaGetLastError());
+  c->stats.kernel_launches++;
+  return 0;
+}
+
+int launch_primary(b200rt_ctx *c, const KernelArgs &A, int trav, bool smem, bool parity, int *tri_out, float *k_out) {
+  switch (trav * 2 + (smem ? 1 : 0)) {
+    case 0: return launch_primary_t<0, false>(c, A, parity, tri_out, k_out);
+    case 1: return launch_primary_t<0, true>(c, A, parity, tri_out, k_out);
+    case 2: return launch_primary_t<1, false>(c, A, parity, tri_out, k_out);
+    case 3: return launch_primary_t<1, true>(c, A, parity, tri_out, k_out);
+    case 4: return launch_primary_t<2, false>(c, A, parity, tri_out, k_out);
+    case 5: return launch_primary_t<2, true>(c, A, parity, tri_out, k_out);
+  }
+  return fail(c, B200RT_ERR_INVALID, "bad traversal mode %d", trav);
+}
+
+template <int TRAV, bool SMEM, bool STATS>
+int launch_paths_t(b200rt_ctx *c, const KernelArgs &A) {
+  auto k = k_paths<TRAV, SMEM, STATS>;
+  size_t smem = smem_bytes(c, SMEM);
+  if (set_smem_attr(c, k, smem)) return B200RT_ERR_CUDA;
+  int grid = 0;
+  if (persistent_grid(c, k, smem, &grid)) return B200RT_ERR_CUDA;
+  int need = (A.n_work + kBlock - 1) / kBlock;
+  if (grid > need) grid = need;
+  k<<<grid, kBlock, smem, c->stream>>>(A);
+  CU(cudaGetLastError());
+  c->stats.kernel_launches++;
+  return 0;
+}
+
+int launch_paths(b200rt_ctx *c, const KernelArgs &A, int trav, bool smem, bool stats) {
+  int key = trav * 4 + (smem ? 2 : 0) + (stats ? 1 : 0);
+  switch (key) {
+    case 0: return launch_paths_t<0, false, false>(c, A);
+    case 1: return launch_paths_t<0, false, true>(c, A);
+    case 2: return launch_paths_t<0, true, false>(c, A);
+    case 3: return launch_paths_t<0, true, true>(c, A);
+    case 4: return launch_paths_t<1, false, false>(c, A);
+    case 5: return launch_paths_t<1, false, true>(c, A);
+    case 6: return launch_paths_t<1, true, false>(c, A);
+    case 7: return launch_paths_t<1, true, true>(c, A);
+    case 8: case 9: return launch_paths_t<2, false, false>(c, A);
+    case 10: case 11: return launch_paths_t<2, true, false>(c, A);
+  }
+  return fail(c, B200RT_ERR_INVALID, "bad traversal mode %d", trav);
+}
+
+template <int TRAV, bool SMEM, bool STATS>
+int launch_trace_t(b200rt_ctx *c, const KernelArgs &A, const float *rays, long long n, int *tri, float *k) {
+  auto kern = k_trace_rays<TRAV, SMEM, STATS>;
+  size_t smem = smem_bytes(c, SMEM);
+  if (set_smem_attr(c, kern, smem)) return B200RT_ERR_CUDA;
+  int grid = 0;
+  if (persistent_grid(c, kern, smem, &grid)) return B200RT_ERR_CUDA;
+  long long need = (n + kBlock - 1) / kBlock;
+  if (grid > need) grid = (int)(need < 1 ? 1 : need);
+  kern<<<grid, kBlock, smem, c->stream>>>(A, rays, n, tri, k);
+  CU(cudaGetLastError());
+  c->stats.kernel_launches++;
+  return 0;
+}
+
+int read_counters(b200rt_ctx *c) {
+  DeviceCounters h;
+  CU(cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->stats.rays = h.rays;
+  c->stats.box_tests = h.box_tests;
+  c->stats.tri_tests = h.tri_tests;
+  c->stats.mismatches = h.mismatches;
+  c->stats.samples = h.samples;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->stats.primary_ms = ms;
+  if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->stats.trace_ms = ms;
+  if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]) == cudaSuccess) c->stats.total_ms = ms;
+  c->stats_pending = false;
+  return 0;
+}
+
+int check_frame_args(b200rt_ctx *c, const float *cam, int width, int height, int spp, int max_bounce,
+                     const b200rt_opts &o, bool need_env, const float *env) {
+  if (!cam) return fail(c, B200RT_ERR_INVALID, "cam is NULL");
+  if (need_env && !env) return fail(c, B200RT_ERR_INVALID, "envData is NULL");
+  if (!c->have_scene) return fail(c, B200RT_ERR_NO_SCENE, "no scene: call b200rt_set_scene first");
+  if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL / 4)
+    return fail(c, B200RT_ERR_INVALID, "bad frame size %d x %d", width, height);
+  if ((int)cam[6] != width)
+    return fail(c, B200RT_ERR_INVALID, "cam[6] = %g but width = %d (the kernel derives rows/columns from cam[6])",
+                (double)cam[6], width);
+  if (spp <= 0) return fail(c, B200RT_ERR_INVALID, "spp must be positive (got %d)", spp);
+  if (max_bounce < 0) return fail(c, B200RT_ERR_INVALID, "maxBounce must be >= 0 (got %d)", max_bounce);
+  if (o.rng_mode != B200RT_RNG_REFERENCE && o.rng_mode != B200RT_RNG_PHILOX)
+    return fail(c, B200RT_ERR_INVALID, "bad rng_mode %d", o.rng_mode);
+  if (o.traversal < 0 || o.traversal > 2) return fail(c, B200RT_ERR_INVALID, "bad traversal %d", o.traversal);
+  if (o.output != B200RT_OUT_FINAL && o.output != B200RT_OUT_SUMS)
+    return fail(c, B200RT_ERR_INVALID, "bad output mode %d", o.output);
+  if (o.sample_end > 0) {
+    if (o.sample_begin < 0 || o.sample_begin >= o.sample_end || o.sample_end > spp)
+      return fail(c, B200RT_ERR_INVALID, "bad sample range [%d,%d) for spp %d", o.sample_begin, o.sample_end, spp);
+    if (o.sample_begin != 0 && o.rng_mode == B200RT_RNG_REFERENCE)
+      return fail(c, B200RT_ERR_INVALID,
+                  "a sample range that does not start at 0 needs B200RT_RNG_PHILOX: the reference generator is one "
+                  "serial stream per pixel");
+    if ((o.sample_begin != 0 || o.sample_end != spp) && o.output != B200RT_OUT_SUMS)
+      return fail(c, B200RT_ERR_INVALID, "a partial sample range only makes sense with B200RT_OUT_SUMS");
+  }
+  if (o.pixel_end > 0 && (o.pixel_begin < 0 || o.pixel_begin >= o.pixel_end || o.pixel_end > width * height))
+    return fail(c, B200RT_ERR_INVALID, "bad pixel range [%d,%d)", o.pixel_begin, o.pixel_end);
+  return 0;
+}
+
+int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp, int max_bounce,
+                const b200rt_opts *opts, float *d_out) {
+  b200rt_opts o;
+  if (opts) o = *opts; else b200rt_default_opts(&o);
+  int rc = check_frame_args(c, cam, width, height, spp, max_bounce, o, true, env);
+  if (rc) return rc;
+  if (!c->have_ibl) return fail(c, B200RT_ERR_NO_SCENE, "no environment map: call b200rt_set_ibl first");
+  CU(cudaSetDevice(c->device));
+  const size_t npix = (size_t)width * height;
+  if (ensure(c, c->d_prim_dirk, npix * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_prim_tri, npix * sizeof(int))) return B200RT_ERR_CUDA;
+  FrameParams F;
+  frame_setup(c, cam, env, width, height, spp, max_bounce, o, &F);
+  KernelArgs A;
+  fill_args(c, F, o, d_out, &A);
+  const int trav = effective_traversal(c, o);
+  const bool smem = use_smem_scene(c);
+  c->stats.kernel_launches = 0;
+  c->stats.scene_in_smem = smem ? 1 : 0;
+  CU(cudaMemsetAsync(c->d_prim_tri.p, 0xff, npix * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
+  CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->stream));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  rc = launch_primary(c, A, trav, smem, false, nullptr, nullptr);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  rc = launch_paths(c, A, trav, smem, o.collect_stats != 0);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  c->stats_pending = true;
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *b200rt_version(void) { return "b200rt 0.1 (sm_100a)"; }
+
+void b200rt_default_opts(b200rt_opts *o) {
+  memset(o, 0, sizeof *o);
+  o->rng_mode = B200RT_RNG_REFERENCE;
+  o->traversal = B200RT_TRAVERSAL_FAST;
+  o->stack_cap = 20;
+  o->output = B200RT_OUT_FINAL;
+}
+
+const char *b200rt_last_error(const b200rt_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int b200rt_create(int device, b200rt_ctx **out) {
+  b200rt_ctx *c = nullptr;
+  if (!out) return fail(nullptr, B200RT_ERR_INVALID, "out_ctx is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, B200RT_ERR_CUDA, "no CUDA device available (%s); b200rt has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= n) return fail(nullptr, B200RT_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, B200RT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, B200RT_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library contains sm_100a code only", device,
+                prop.major, prop.minor);
+  c = new b200rt_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  memset(&c->stats, 0, sizeof c->stats);
+  auto bail = [&](const char *what, cudaError_t err) {
+    fail(nullptr, B200RT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+    delete c;
+    return B200RT_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (int i = 0; i < 3; ++i)
+    if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaMalloc(&c->d_counters, sizeof(DeviceCounters))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&c->d_work, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
+  *out = c;
+  return 0;
+}
+
+void b200rt_destroy(b200rt_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_mats, &c->d_bvh9, &c->d_prim_dirk,
+                    &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b};
+  for (DevBuf *b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (c->ibl_tex) cudaDestroyTextureObject(c->ibl_tex);
+  if (c->ibl_array) cudaFreeArray(c->ibl_array);
+  if (c->d_counters) cudaFree(c->d_counters);
+  if (c->d_work) cudaFree(c->d_work);
+  for (int i = 0; i < 3; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int b200rt_set_materials(b200rt_ctx *c, const float *mat, int64_t n_mat) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!mat || n_mat <= 0 || n_mat % 6) return fail(c, B200RT_ERR_INVALID, "material_data must hold 6 floats per material (got %lld)", (long long)n_mat);
+  const int nm = (int)(n_mat / 6);
+  for (int m = 0; m < nm; ++m) {
+    float t = mat[6 * m];
+    if (!(t >= 0.0f && t < 4.0f))
+      return fail(c, B200RT_ERR_INVALID, "material %d has type %g; the kernel defines types 0..3 only (Raytracing.cl:58-78)", m, (double)t);
+  }
+  for (int32_t m : c->tri_mat)
+    if (m < 0 || m >= nm) return fail(c, B200RT_ERR_INVALID, "a triangle uses material %d but only %d materials were given", m, nm);
+  CU(cudaSetDevice(c->device));
+  uint64_t h = hash_bytes(mat, (size_t)n_mat * 4, 0x6d617473ull);
+  if (c->n_mats == nm && h == c->mat_hash && c->d_mats.p) return 0;
+  if (ensure(c, c->d_mats, (size_t)n_mat * 4)) return B200RT_ERR_CUDA;
+  CU(cudaMemcpyAsync(c->d_mats.p, mat, (size_t)n_mat * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->n_mats = nm;
+  c->mat_hash = h;
+  return 0;
+}
+
+int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const float *vuv,
+                     int64_t n_vuv, const int32_t *face, int64_t n_face, const float *mat, int64_t n_mat,
+                     const int32_t *light, int64_t n_light, const float *bvh, int64_t n_bvh) {
+  (void)vuv; (void)n_vuv; (void)light; (void)n_light;  // fetched / passed but never used by the kernel (MathLib.cl:217, Raytracing.cl:163)
+  if (!c) return B200RT_ERR_INVALID;
+  auto t0 = std::chrono::steady_clock::now();
+  if (!vp || !vn || !face || !mat || !bvh) return fail(c, B200RT_ERR_INVALID, "NULL scene buffer");
+  if (n_vp <= 0 || n_vp % 3) return fail(c, B200RT_ERR_INVALID, "vertex_p length %lld is not a positive multiple of 3", (long long)n_vp);
+  if (n_vn <= 0 || n_vn % 3) return fail(c, B200RT_ERR_INVALID, "vertex_n length %lld is not a positive multiple of 3", (long long)n_vn);
+  if (n_face <= 0 || n_face % 10) return fail(c, B200RT_ERR_INVALID, "face_data length %lld is not a positive multiple of 10", (long long)n_face);
+  if (n_bvh <= 0 || n_bvh % 9) return fail(c, B200RT_ERR_INVALID, "BVH length %lld is not a positive multiple of 9", (long long)n_bvh);
+  if (n_bvh / 9 >= (1 << 24)) return fail(c, B200RT_ERR_UNSUPPORTED, "%lld nodes: float32-encoded child indices are exact only below 2^24 (BVH.py:165)", (long long)(n_bvh / 9));
+  if (n_mat <= 0 || n_mat % 6) return fail(c, B200RT_ERR_INVALID, "material_data must hold 6 floats per material (got %lld)", (long long)n_mat);
+
+  uint64_t h = 0x7363656e65ull;
+  h = hash_bytes(vp, (size_t)n_vp * 4, h);
+  h = hash_bytes(vn, (size_t)n_vn * 4, h);
+  h = hash_bytes(face, (size_t)n_face * 4, h);
+  h = hash_bytes(bvh, (size_t)n_bvh * 4, h);
+  if (c->have_scene && h == c->scene_hash) {  // geometry unchanged (the UI rebuilds identical arrays per render, UI.py:98)
+    int rc = b200rt_set_materials(c, mat, n_mat);
+    c->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+  }
+
+  const int n_nodes = (int)(n_bvh / 9), n_tris = (int)(n_face / 10);
+  const int nvp = (int)(n_vp / 3), nvn = (int)(n_vn / 3), nm = (int)(n_mat / 6);
+
+  // ---- triangles: validate indices, precompute edges exactly as MathLib.cl:129-130 rounds them -------------
+  std::vector<float4> tris((size_t)n_tris * 3), normals((size_t)n_tris);
+  std::vector<int32_t> tri_mat((size_t)n_tris);
+  float cmax = 0.0f, cmin_nz = INFINITY;
+  for (int t = 0; t < n_tris; ++t) {
+    const int32_t *f = face + 10 * (size_t)t;
+    for (int j = 7; j < 10; ++j)
+      if (f[j] < 0 || f[j] >= nvp) return fail(c, B200RT_ERR_INVALID, "triangle %d: position index %d out of range [0,%d)", t, f[j], nvp);
+    if (f[4] < 0 || f[4] >= nvn) return fail(c, B200RT_ERR_INVALID, "triangle %d: normal index %d out of range [0,%d)", t, f[4], nvn);
+    if (f[0] < 0 || f[0] >= nm) return fail(c, B200RT_ERR_INVALID, "triangle %d: material %d out of range [0,%d)", t, f[0], nm);
+    const float *a = vp + 3 * (size_t)f[7], *b = vp + 3 * (size_t)f[8], *cc = vp + 3 * (size_t)f[9];
+    v3 A = mk3(a[0], a[1], a[2]);
+    v3 e1 = mk3(b[0], b[1], b[2]) - A;
+    v3 e2 = mk3(cc[0], cc[1], cc[2]) - A;
+    tris[3 * (size_t)t + 0] = make_float4(A.x, A.y, A.z, e1.x);
+    tris[3 * (size_t)t + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    float matbits, rankbits;
+    int32_t m = f[0], r = 0x7fffffff;
+    memcpy(&matbits, &m, 4);
+    memcpy(&rankbits, &r, 4);
+    tris[3 * (size_t)t + 2] = make_float4(e2.z, matbits, rankbits, 0.0f);
+    const float *n0 = vn + 3 * (size_t)f[4];
+    normals[t] = make_float4(n0[0], n0[1], n0[2], 0.0f);
+    tri_mat[t] = m;
+    for (int j = 7; j < 10; ++j)
+      for (int k = 0; k < 3; ++k) {
+        float v = std::fabs(vp[3 * (size_t)f[j] + k]);
+        if (!(v <= cmax)) cmax = v;  // also catches NaN
+      }
+  }
+
+  // ---- nodes: validate, detect tree shape, rank leaves in the reference's visiting order -----------------------
+  std::vector<int> inner_id((size_t)n_nodes, -1), level((size_t)n_nodes, 0);
+  std::vector<unsigned char> seen((size_t)n_nodes, 0);
+  bool canonical = true;
+  auto L = [&](int i) { return (int)bvh[9 * (size_t)i]; };
+  auto R = [&](int i) { return (int)bvh[9 * (size_t)i + 1]; };
+  auto T = [&](int i) { return (int)bvh[9 * (size_t)i + 8]; };
+  {
+    // right-first pre-order walk == the order MathLib.cl:252-280 pops nodes when every box test passes
+    std::vector<int> stack;
+    stack.push_back(0);
+    int rank = 0, depth = 0;
+    size_t max_stack = 1;
+    while (!stack.empty()) {
+      int cur = stack.back();
+      stack.pop_back();
+      if (cur < 0 || cur >= n_nodes) return fail(c, B200RT_ERR_INVALID, "BVH child index %d out of range [0,%d)", cur, n_nodes);
+      if (seen[cur]) return fail(c, B200RT_ERR_INVALID, "BVH node %d is reachable twice: not a tree (the traversal would not terminate)", cur);
+      seen[cur] = 1;
+      int l = L(cur), r = R(cur), t = T(cur);
+      if (t < -1 || t >= n_tris) return fail(c, B200RT_ERR_INVALID, "BVH node %d: triangle %d out of range [0,%d)", cur, t, n_tris);
+      if (l < -1 || r < -1) return fail(c, B200RT_ERR_INVALID, "BVH node %d: negative child index", cur);
+      for (int k = 2; k < 8; ++k) {
+        float v = std::fabs(bvh[9 * (size_t)cur + k]);
+        if (!(v <= cmax)) cmax = v;
+        if (v > 0.0f && v < cmin_nz) cmin_nz = v;
+      }
+      bool leaf = (t != -1 && l == -1 && r == -1), inner = (t == -1 && l != -1 && r != -1);
+      if (!leaf && !inner) canonical = false;
+      if (t != -1) {
+        int32_t old;
+        memcpy(&old, &tris[3 * (size_t)t + 2].z, 4);
+        if (old == 0x7fffffff) memcpy(&tris[3 * (size_t)t + 2].z, &rank, 4);
+        ++rank;
+      }
+      if (level[cur] > depth) depth = level[cur];
+      if (l != -1) { stack.push_back(l); if (l >= 0 && l < n_nodes) level[l] = level[cur] + 1; }
+      if (r != -1) { stack.push_back(r); if (r >= 0 && r < n_nodes) level[r] = level[cur] + 1; }
+      if (stack.size() > max_stack) max_stack = stack.size();
+    }
+    c->depth = depth;
+    c->ref_stack_need = (int)max_stack;
+  }
+  if (!(cmax < INFINITY)) return fail(c, B200RT_ERR_INVALID, "scene contains a non-finite coordinate");
+
+  // ---- repack interior nodes breadth-first into the 64-byte two-child layout --------------------------------------
+  std::vector<float4> nodes;
+  int n_inner = 0;
+  int root_ref = 0;
+  if (canonical) {
+    if (T(0) != -1) {
+      root_ref = ~T(0);
+    } else {
+      std::vector<int> order;
+      order.reserve((size_t)n_nodes / 2 + 1);
+      order.push_back(0);
+      inner_id[0] = 0;
+      for (size_t q = 0; q < order.size(); ++q) {
+        int cur = order[q];
+        int ch[2] = {L(cur), R(cur)};
+        for (int k = 0; k < 2; ++k)
+          if (T(ch[k]) == -1) {
+            inner_id[ch[k]] = (int)order.size();
+            order.push_back(ch[k]);
+          }
+      }
+      n_inner = (int)order.size();
+      nodes.resize((size_t)n_inner * 4);
+      for (int q = 0; q < n_inner; ++q) {
+        int cur = order[q];
+        int l = L(cur), r = R(cur);
+        const float *bl = bvh + 9 * (size_t)l, *br = bvh + 9 * (size_t)r;
+        int32_t refl = T(l) != -1 ? ~T(l) : inner_id[l];
+        int32_t refr = T(r) != -1 ? ~T(r) : inner_id[r];
+        float fl, fr;
+        memcpy(&fl, &refl, 4);
+        memcpy(&fr, &refr, 4);
+        nodes[4 * (size_t)q + 0] = make_float4(bl[2], bl[3], bl[4], bl[5]);
+        nodes[4 * (size_t)q + 1] = make_float4(bl[6], bl[7], br[2], br[3]);
+        nodes[4 * (size_t)q + 2] = make_float4(br[4], br[5], br[6], br[7]);
+        nodes[4 * (size_t)q + 3] = make_float4(fl, fr, 0.0f, 0.0f);
+      }
+    }
+  }
+  for (int k = 0; k < 6; ++k) c->root_box[k] = bvh[2 + k];
+  {
+    float dx = bvh[5] - bvh[2], dy = bvh[6] - bvh[3], dz = bvh[7] - bvh[4];
+    c->cull_abs = 1e-3f * std::sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  c->fast_div_ok = (cmax <= 1.099511627776e12f && cmin_nz >= 8.673617379884035e-19f /* 2^-60 */) ? 1 : 0;
+
+  // ---- upload -------------------------------------------------------------------------------------------------------------
+  CU(cudaSetDevice(c->device));
+  if (ensure(c, c->d_tris, tris.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_normals, normals.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_nodes, nodes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_bvh9, (size_t)n_bvh * 4)) return B200RT_ERR_CUDA;
+  CU(cudaMemcpyAsync(c->d_tris.p, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_normals.p, normals.data(), normals.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  if (!nodes.empty())
+    CU(cudaMemcpyAsync(c->d_nodes.p, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_bvh9.p, bvh, (size_t)n_bvh * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->n_nodes9 = n_nodes;
+  c->n_inner = n_inner;
+  c->n_tris = n_tris;
+  c->canonical = canonical;
+  c->root_ref = root_ref;
+  c->tri_mat.swap(tri_mat);
+  c->have_scene = false;
+  c->mat_hash = 0;
+  c->n_mats = 0;
+  int rc = b200rt_set_materials(c, mat, n_mat);
+  if (rc) return rc;
+  c->have_scene = true;
+  c->scene_hash = h;
+  c->stats.nodes = n_nodes;
+  c->stats.triangles = n_tris;
+  c->stats.bvh_depth = c->depth;
+  c->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+int b200rt_set_ibl(b200rt_ctx *c, const uint8_t *rgba, int width, int height) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!rgba || width <= 0 || height <= 0) return fail(c, B200RT_ERR_INVALID, "bad environment map (%p, %d x %d)", (const void *)rgba, width, height);
+  if (width > 131072 || height > 65536) return fail(c, B200RT_ERR_UNSUPPORTED, "environment map %d x %d exceeds the 2-D texture limits", width, height);
+  auto t0 = std::chrono::steady_clock::now();
+  uint64_t h = hash_bytes(rgba, (size_t)width * height * 4, 0x69626cull);
+  if (c->have_ibl && h == c->ibl_hash && width == c->ibl_w && height == c->ibl_h) return 0;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->ibl_tex) { cudaDestroyTextureObject(c->ibl_tex); c->ibl_tex = 0; }
+  if (c->ibl_array) { cudaFreeArray(c->ibl_array); c->ibl_array = nullptr; }
+  c->have_ibl = false;
+  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+  CU(cudaMallocArray(&c->ibl_array, &fmt, (size_t)width, (size_t)height));
+  CU(cudaMemcpy2DToArrayAsync(c->ibl_array, 0, 0, rgba, (size_t)width * 4, (size_t)width * 4, (size_t)height,
+                              cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaResourceDesc res;
+  memset(&res, 0, sizeof res);
+  res.resType = cudaResourceTypeArray;
+  res.res.array.array = c->ibl_array;
+  cudaTextureDesc td;
+  memset(&td, 0, sizeof td);
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;  // CLK_ADDRESS_CLAMP_TO_EDGE (Raytracing.cl:179)
+  td.filterMode = cudaFilterModePoint;                          // integer coordinates address single texels
+  td.readMode = cudaReadModeElementType;                        // raw bytes; the kernel divides by 255 itself
+  td.normalizedCoords = 0;                                      // CLK_NORMALIZED_COORDS_FALSE
+  CU(cudaCreateTextureObject(&c->ibl_tex, &res, &td, nullptr));
+  c->ibl_w = width;
+  c->ibl_h = height;
+  c->ibl_hash = h;
+  c->have_ibl = true;
+  c->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+int b200rt_render_device(b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp,
+                         int max_bounce, const b200rt_opts *opts, float *d_out) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!d_out) return fail(c, B200RT_ERR_INVALID, "d_out_rgb is NULL");
+  return render_impl(c, cam, env, width, height, spp, max_bounce, opts, d_out);
+}
+
+int b200rt_render(b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp, int max_bounce,
+                  const b200rt_opts *opts, float *out) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!out) return fail(c, B200RT_ERR_INVALID, "out_rgb is NULL");
+  if (width <= 0 || height <= 0) return fail(c, B200RT_ERR_INVALID, "bad frame size %d x %d", width, height);
+  const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+  CU(cudaSetDevice(c->device));
+  if (ensure(c, c->d_out, bytes)) return B200RT_ERR_CUDA;
+  CU(cudaMemsetAsync(c->d_out.p, 0, bytes, c->stream));
+  int rc = render_impl(c, cam, env, width, height, spp, max_bounce, opts, static_cast<float *>(c->d_out.p));
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, c->d_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));  // blocking read-back, KernelLauncher.py:78
+  CU(cudaStreamSynchronize(c->stream));
+  return read_counters(c);
+}
+
+int b200rt_sync(b200rt_ctx *c) {
+  if (!c) return B200RT_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->stats_pending) return read_counters(c);
+  return 0;
+}
+
+int b200rt_finalize_device(b200rt_ctx *c, const float *d_sums, float *d_out, int64_t n_pixels, int spp) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!d_sums || !d_out || n_pixels <= 0 || spp <= 0) return fail(c, B200RT_ERR_INVALID, "bad finalize arguments");
+  CU(cudaSetDevice(c->device));
+  long long n = (long long)n_pixels * 3;
+  int grid = (int)std::min<long long>((n + 255) / 256, (long long)c->sm_count * 8);
+  k_finalize<<<grid, 256, 0, c->stream>>>(d_sums, d_out, n, (float)spp);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int b200rt_reduce_finalize_device(b200rt_ctx *c, const float *const *d_parts, int n_parts, float *d_out,
+                                  int64_t n_pixels, int spp) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!d_parts || n_parts < 1 || n_parts > 16 || !d_out || n_pixels <= 0 || spp <= 0)
+    return fail(c, B200RT_ERR_INVALID, "bad reduce_finalize arguments (1..16 parts)");
+  CU(cudaSetDevice(c->device));
+  PartList pl;
+  pl.n = n_parts;
+  bool aligned = (reinterpret_cast<uintptr_t>(d_out) % 16) == 0;
+  for (int i = 0; i < n_parts; ++i) {
+    if (!d_parts[i]) return fail(c, B200RT_ERR_INVALID, "part %d is NULL", i);
+    pl.p[i] = d_parts[i];
+    aligned = aligned && (reinterpret_cast<uintptr_t>(d_parts[i]) % 16) == 0;
+  }
+  long long n = (long long)n_pixels * 3;
+  long long n4 = aligned ? n / 4 : 0;
+  int grid = (int)std::min<long long>((n / 4 + 255) / 256 + 1, (long long)c->sm_count * 8);
+  k_reduce_finalize<<<grid, 256, 0, c->stream>>>(pl, d_out, n4, n, (float)spp);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int b200rt_primary_hits(b200rt_ctx *c, const float *cam, int width, int height, const b200rt_opts *opts,
+                        int32_t *tri_out, float *k_out) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!tri_out || !k_out) return fail(c, B200RT_ERR_INVALID, "NULL output");
+  b200rt_opts o;
+  if (opts) o = *opts; else b200rt_default_opts(&o);
+  int rc = check_frame_args(c, cam, width, height, 1, 0, o, false, nullptr);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  const size_t npix = (size_t)width * height;
+  if (ensure(c, c->d_tmp_a, npix * sizeof(int))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tmp_b, npix * sizeof(float))) return B200RT_ERR_CUDA;
+  FrameParams F;
+  frame_setup(c, cam, nullptr, width, height, 1, 0, o, &F);
+  KernelArgs A;
+  fill_args(c, F, o, nullptr, &A);
+  c->stats.kernel_launches = 0;
+  CU(cudaMemsetAsync(c->d_tmp_a.p, 0xff, npix * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->d_tmp_b.p, 0, npix * sizeof(float), c->stream));
+  CU(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  rc = launch_primary(c, A, effective_traversal(c, o), use_smem_scene(c), true, static_cast<int *>(c->d_tmp_a.p),
+                      static_cast<float *>(c->d_tmp_b.p));
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  CU(cudaMemcpyAsync(tri_out, c->d_tmp_a.p, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(k_out, c->d_tmp_b.p, npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return read_counters(c);
+}
+
+int b200rt_trace_rays(b200rt_ctx *c, const float *rays, int64_t n, const b200rt_opts *opts, int32_t *tri_out, float *k_out) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!rays || !tri_out || !k_out || n <= 0) return fail(c, B200RT_ERR_INVALID, "bad trace_rays arguments");
+  if (!c->have_scene) return fail(c, B200RT_ERR_NO_SCENE, "no scene: call b200rt_set_scene first");
+  b200rt_opts o;
+  if (opts) o = *opts; else b200rt_default_opts(&o);
+  if (o.traversal < 0 || o.traversal > 2) return fail(c, B200RT_ERR_INVALID, "bad traversal %d", o.traversal);
+  CU(cudaSetDevice(c->device));
+  if (ensure(c, c->d_misc, (size_t)n * 6 * sizeof(float))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tmp_a, (size_t)n * sizeof(int))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tmp_b, (size_t)n * sizeof(float))) return B200RT_ERR_CUDA;
+  CU(cudaMemcpyAsync(c->d_misc.p, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
+  FrameParams F;
+  memset(&F, 0, sizeof F);
+  KernelArgs A;
+  fill_args(c, F, o, nullptr, &A);
+  c->stats.kernel_launches = 0;
+  const float *dr = static_cast<const float *>(c->d_misc.p);
+  int *dt = static_cast<int *>(c->d_tmp_a.p);
+  float *dk = static_cast<float *>(c->d_tmp_b.p);
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  int rc;
+  const bool smem = use_smem_scene(c), st = o.collect_stats != 0;
+  const int trav = effective_traversal(c, o);
+  if (trav == 0) rc = smem ? (st ? launch_trace_t<0, true, true>(c, A, dr, n, dt, dk) : launch_trace_t<0, true, false>(c, A, dr, n, dt, dk))
+                           : (st ? launch_trace_t<0, false, true>(c, A, dr, n, dt, dk) : launch_trace_t<0, false, false>(c, A, dr, n, dt, dk));
+  else if (trav == 1) rc = smem ? (st ? launch_trace_t<1, true, true>(c, A, dr, n, dt, dk) : launch_trace_t<1, true, false>(c, A, dr, n, dt, dk))
+                                : (st ? launch_trace_t<1, false, true>(c, A, dr, n, dt, dk) : launch_trace_t<1, false, false>(c, A, dr, n, dt, dk));
+  else rc = smem ? launch_trace_t<2, true, false>(c, A, dr, n, dt, dk) : launch_trace_t<2, false, false>(c, A, dr, n, dt, dk);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  CU(cudaMemcpyAsync(tri_out, dt, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(k_out, dk, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  rc = read_counters(c);
+  c->stats.rays = (uint64_t)n;
+  return rc;
+}
+
+int b200rt_img_processing(b200rt_ctx *c, const float *src, float *dst, int64_t n, int64_t global) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!src || !dst || global <= 0 || n < 0) return fail(c, B200RT_ERR_INVALID, "bad img_processing arguments");
+  CU(cudaSetDevice(c->device));
+  size_t bytes = (size_t)global * sizeof(float);
+  if (ensure(c, c->d_tmp_a, bytes)) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tmp_b, bytes)) return B200RT_ERR_CUDA;
+  CU(cudaMemcpyAsync(c->d_tmp_a.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  // work-items with i >= n leave dst untouched: start from the caller's dst contents
+  CU(cudaMemcpyAsync(c->d_tmp_b.p, dst, bytes, cudaMemcpyHostToDevice, c->stream));
+  int grid = (int)std::min<long long>(((long long)global + 255) / 256, (long long)c->sm_count * 16);
+  k_img_processing<<<grid, 256, 0, c->stream>>>(static_cast<const float *>(c->d_tmp_a.p), static_cast<float *>(c->d_tmp_b.p),
+                                                 (long long)n, (long long)global);
+  CU(cudaGetLastError());
+  c->stats.kernel_launches = 1;
+  CU(cudaMemcpyAsync(dst, c->d_tmp_b.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int b200rt_get_stats(const b200rt_ctx *c, b200rt_stats *s) {
+  if (!c || !s) return B200RT_ERR_INVALID;
+  if (c->stats_pending) {
+    int rc = b200rt_sync(const_cast<b200rt_ctx *>(c));
+    if (rc) return rc;
+  }
+  *s = c->stats;
+  return 0;
+}
+
+int b200rt_math_probe(b200rt_ctx *c, int fn, const float *a, const float *b, int64_t n, float *out) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!a || !out || n <= 0 || fn < 0 || fn > 10) return fail(c, B200RT_ERR_INVALID, "bad math_probe arguments");
+  CU(cudaSetDevice(c->device));
+  size_t bytes = (size_t)n * sizeof(float);
+  if (ensure(c, c->d_tmp_a, bytes)) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tmp_b, bytes)) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_misc, bytes)) return B200RT_ERR_CUDA;
+  CU(cudaMemcpyAsync(c->d_tmp_a.p, a, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (b) CU(cudaMemcpyAsync(c->d_tmp_b.p, b, bytes, cudaMemcpyHostToDevice, c->stream));
+  else CU(cudaMemsetAsync(c->d_tmp_b.p, 0, bytes, c->stream));
+  k_math_probe<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(fn, static_cast<const float *>(c->d_tmp_a.p),
+                                                                    static_cast<const float *>(c->d_tmp_b.p), (long long)n,
+                                                                    static_cast<float *>(c->d_misc.p));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, c->d_misc.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int b200rt_philox_probe(b200rt_ctx *c, const uint32_t ctr[4], uint32_t key0, uint32_t key1, uint32_t out[4]) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!ctr || !out) return fail(c, B200RT_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  if (ensure(c, c->d_misc, 16)) return B200RT_ERR_CUDA;
+  k_philox_probe<<<1, 1, 0, c->stream>>>(ctr[0], ctr[1], ctr[2], ctr[3], key0, key1, static_cast<uint32_t *>(c->d_misc.p));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, c->d_misc.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int b200rt_ipc_export(b200rt_ctx *c, const void *d_ptr, uint8_t handle_out[64]) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!d_ptr || !handle_out) return fail(c, B200RT_ERR_INVALID, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+  memcpy(handle_out, &h, 64);
+  return 0;
+}
+
+int b200rt_ipc_open(b200rt_ctx *c, const uint8_t handle[64], void **d_ptr_out) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!handle || !d_ptr_out) return fail(c, B200RT_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int b200rt_ipc_close(b200rt_ctx *c, void *d_ptr) {
+  if (!c) return B200RT_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+}
+
+}  // extern "C"

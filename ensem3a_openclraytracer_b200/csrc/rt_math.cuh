@@ -1,0 +1,171 @@
+// Device arithmetic of the b200rt kernels.
+//
+// Numerical contract (DESIGN.md "Arithmetic"): every + - * / sqrt is IEEE binary32
+// round-to-nearest and is never contracted (this translation unit is compiled with
+// -fmad=false; FMAs appear only where written as __fmaf_rn), dot products are summed
+// left to right, normalize divides, and the transcendental built-ins of the reference
+// kernels (cos sin acos asin atan2 powr; MathLib.cl) are CORRECTLY ROUNDED binary32,
+// obtained by evaluating in binary64 and rounding once.  B200 runs binary64 at half the
+// binary32 rate, so this costs a few percent of a path and buys results that are
+// independent of any vendor's float libm.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200rt {
+
+struct v3 {
+  float x, y, z;
+};
+struct quat {
+  float w, x, y, z;
+};
+
+#define RT_DEV __device__ __forceinline__
+#define RT_HD __host__ __device__ __forceinline__
+
+RT_HD v3 mk3(float x, float y, float z) {
+  v3 r;
+  r.x = x; r.y = y; r.z = z;
+  return r;
+}
+RT_HD v3 operator+(v3 a, v3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_HD v3 operator-(v3 a, v3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_HD v3 operator*(v3 a, v3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_HD v3 operator*(v3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+RT_HD v3 operator/(v3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+RT_HD v3 neg3(v3 a) { return mk3(-a.x, -a.y, -a.z); }
+RT_HD float dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RT_HD v3 cross(v3 a, v3 b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+RT_HD v3 unit(v3 a) { return a / sqrtf(dot(a, a)); }
+
+// ---- correctly-rounded binary32 transcendentals (binary64 evaluation, one rounding) ----
+RT_DEV float cr_sin(float a) { return __double2float_rn(sin((double)a)); }
+RT_DEV float cr_cos(float a) { return __double2float_rn(cos((double)a)); }
+RT_DEV void cr_sincos(float a, float *s, float *c) {
+  double ds, dc;
+  sincos((double)a, &ds, &dc);
+  *s = __double2float_rn(ds);
+  *c = __double2float_rn(dc);
+}
+RT_DEV float cr_tan(float a) { return __double2float_rn(tan((double)a)); }
+RT_DEV float cr_acos(float a) { return __double2float_rn(acos((double)a)); }
+RT_DEV float cr_asin(float a) { return __double2float_rn(asin((double)a)); }
+RT_DEV float cr_atan2(float y, float x) { return __double2float_rn(atan2((double)y, (double)x)); }
+RT_DEV float cr_pow(float a, float b) { return __double2float_rn(pow((double)a, (double)b)); }
+
+// ---- quaternion rotation, MathLib.cl:51-65 ------------------------------------------------
+RT_HD quat qmul(quat q, quat p) {
+  v3 qv = mk3(q.x, q.y, q.z), pv = mk3(p.x, p.y, p.z);
+  quat r;
+  r.w = q.w * p.w - dot(qv, pv);
+  v3 t = ((qv * p.w) + (pv * q.w)) + cross(qv, pv);
+  r.x = t.x; r.y = t.y; r.z = t.z;
+  return r;
+}
+
+// The pair (q, normalised scaled conjugate) the reference builds for one rotateVec call.
+struct rotor {
+  quat q, qi;
+};
+
+RT_HD rotor make_rotor(float c, float s, v3 axis) {  // c = cos(angle/2), s = sin(angle/2), correctly rounded
+  v3 sv = unit(axis) * s;
+  rotor r;
+  r.q.w = c; r.q.x = sv.x; r.q.y = sv.y; r.q.z = sv.z;
+  float n2 = c * c + dot(sv, sv);
+  v3 ng = sv * (-1.0f);
+  float uw = c * n2, ux = ng.x * n2, uy = ng.y * n2, uz = ng.z * n2;
+  float len = sqrtf(uw * uw + ux * ux + uy * uy + uz * uz);
+  r.qi.w = uw / len; r.qi.x = ux / len; r.qi.y = uy / len; r.qi.z = uz / len;
+  return r;
+}
+
+RT_HD v3 apply_rotor(const rotor &r, v3 v) {
+  quat p;
+  p.w = 0.0f; p.x = v.x; p.y = v.y; p.z = v.z;
+  quat o = qmul(qmul(r.q, p), r.qi);
+  return mk3(o.x, o.y, o.z);
+}
+
+RT_DEV v3 rotate_about(float angle, v3 axis, v3 v) {
+  float s, c;
+  cr_sincos(angle * 0.5f, &s, &c);
+  rotor r = make_rotor(c, s, axis);
+  return apply_rotor(r, v);
+}
+
+// ---- random numbers ---------------------------------------------------------------------------
+RT_HD float bits_to_unit(uint32_t bits) {  // MathLib.cl:302-309
+#ifdef __CUDA_ARCH__
+  float f = __uint_as_float((bits & 0x007fffffu) | 0x40000000u);
+#else
+  union { float f; uint32_t u; } cvt;
+  cvt.u = (bits & 0x007fffffu) | 0x40000000u;
+  float f = cvt.f;
+#endif
+  return (f - 2.0f) / 2.0f;
+}
+
+RT_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Two uniform draws for bounce `j` of sample `s` of pixel `i`.
+struct rng_state {
+  uint32_t a;  // reference generator: the kernel's seed0 word (its seed1 is write-only, see rt_oracle.c)
+};
+
+template <int RNG>
+RT_DEV void draw2(rng_state &g, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t k0, uint32_t k1,
+                  float *u0, float *u1) {
+  if (RNG == 0) {
+    uint32_t b = 36969u * (g.a & 65535u) + (g.a >> 16);
+    uint32_t a = 18000u * (b & 65535u) + (b >> 16);
+    *u0 = bits_to_unit((b << 16) + a);
+    b = 36969u * (a & 65535u) + (a >> 16);
+    a = 18000u * (b & 65535u) + (b >> 16);
+    *u1 = bits_to_unit((b << 16) + a);
+    g.a = a;
+  } else {
+    uint32_t o[4];
+    philox4x32_10(pixel, sample, bounce, 0u, k0, k1, o);
+    *u0 = bits_to_unit(o[0]);
+    *u1 = bits_to_unit(o[1]);
+  }
+}
+
+// ---- exact division by a per-ray constant -----------------------------------------------------------
+// q = RN(x / d) from r = RN(1/d): one multiply and two FMA correction steps.  After the first step q
+// is a faithful rounding of x/d; with a correctly-rounded reciprocal the second step is then the
+// correctly-rounded quotient (Markstein).  Valid when d, r and the quotient are normal and finite —
+// the traversal checks the ray's direction once (ray_div_safe) and falls back to true division
+// otherwise.  The sign of a zero quotient may differ from IEEE; the slab test only compares.
+RT_DEV float div_by(float x, float d, float r) {
+  float q = x * r;
+  float e = __fmaf_rn(-q, d, x);
+  q = __fmaf_rn(e, r, q);
+  e = __fmaf_rn(-q, d, x);
+  return __fmaf_rn(e, r, q);
+}
+
+RT_DEV bool div_safe(float d) {
+  float a = fabsf(d);
+  return a >= 9.094947017729282e-13f /* 2^-40 */ && a <= 1.099511627776e12f /* 2^40 */;
+}
+
+}  // namespace b200rt

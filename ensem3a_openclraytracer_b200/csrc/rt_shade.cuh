@@ -1,0 +1,138 @@
+// Camera rays, direction sampling, BSDFs and the environment lookup of the b200rt kernels.
+// Each function follows the reference statement by statement in rounding order
+// (file:line given per function); see rt_math.cuh for the arithmetic contract.
+#pragma once
+#include "rt_math.cuh"
+
+namespace b200rt {
+
+// Everything that is constant over one frame.  The transcendental parts (camera / sun / environment
+// rotations, focal distance) are evaluated once on the host by frame_setup() in b200rt_api.cu with
+// the same correctly-rounded definitions; the reference re-derives them per ray.
+struct FrameParams {
+  int width, height;
+  v3 cam_pos;
+  float focal_off;  // 1 / (2 tan(fov/2)), Raytracing.cl:24
+  float step;       // (float)(1.0 / cam[6]), Raytracing.cl:27
+  rotor cam_rx, cam_ry, cam_rz;
+  v3 sun_dir;       // Raytracing.cl:115-118
+  float sun_power, ibl_power;
+  rotor ibl_r1, ibl_r2;  // MathLib.cl:73-74
+  int ibl_w, ibl_h;
+  int spp, max_bounce;
+  int s0, s1;
+  int pixel_begin, pixel_end;
+  int out_mode;
+  int rng_mode;
+  uint32_t key0, key1;
+};
+
+struct Material {
+  int type;
+  v3 color;
+  float roughness;
+};
+
+RT_DEV Material load_material(const float *mats, int idx) {  // Raytracing.cl:5-15
+  const float *m = mats + 6 * idx;
+  Material r;
+  r.type = (int)__ldg(m);
+  r.color = mk3(__ldg(m + 1), __ldg(m + 2), __ldg(m + 3));
+  r.roughness = __ldg(m + 4);
+  return r;
+}
+
+// Raytracing.cl:18-37
+RT_DEV v3 camera_dir(const FrameParams &F, int i) {
+  int col = (i + 1) % F.width;
+  int row = (i - col) / F.width;
+  v3 focal = mk3(F.cam_pos.x, F.cam_pos.y - F.focal_off, F.cam_pos.z);
+  v3 pix = mk3((float)col * F.step - 0.5f, 0.0f, 0.5f - (float)row * F.step);
+  v3 d = unit((F.cam_pos + pix) - focal);
+  d = apply_rotor(F.cam_rx, d);
+  d = apply_rotor(F.cam_ry, d);
+  d = apply_rotor(F.cam_rz, d);
+  return d;
+}
+
+// MathLib.cl:72-90.  Integer texel coordinates through a clamp-to-edge sampler; UNORM8 -> b/255.
+RT_DEV v3 ibl_lookup(const FrameParams &F, cudaTextureObject_t tex, v3 dir) {
+  dir = apply_rotor(F.ibl_r1, dir);
+  dir = apply_rotor(F.ibl_r2, dir);
+  float u = cr_atan2(dir.z, dir.x) * 0.1591f + 0.5f;
+  float v = cr_asin(dir.y) * 0.3183f + 0.5f;
+  int px = __float2int_rz(u * (float)F.ibl_w);
+  int py = __float2int_rz(v * (float)F.ibl_h);
+  px = max(0, min(px, F.ibl_w - 1));
+  py = max(0, min(py, F.ibl_h - 1));
+  uchar4 t = tex2D<uchar4>(tex, (float)px + 0.5f, (float)py + 0.5f);
+  return mk3(__fdiv_rn((float)t.x, 255.0f), __fdiv_rn((float)t.y, 255.0f), __fdiv_rn((float)t.z, 255.0f)) * 1.0f;
+}
+
+// frame that takes the local +Z hemisphere onto normal n — shared by both samplers
+// (MathLib.cl:325-336 and :349-361).  normalise_axis: the uniform sampler normalises the axis before
+// rotateVec (which normalises again), the cosine sampler does not.
+RT_DEV v3 to_world(v3 local, v3 n, bool normalise_axis) {
+  const v3 zup = mk3(0.0f, 0.0f, 1.0f);
+  if (fabsf(dot(unit(n), zup)) == 1.0f) return local * n.z;
+  v3 axis = cross(zup, n);
+  if (normalise_axis) axis = unit(axis);
+  float ang = cr_acos(dot(n, zup));
+  return rotate_about(ang, axis, local);
+}
+
+// MathLib.cl:313-339
+RT_DEV v3 sample_cosine(v3 n, float u, float u2, float *inv_pdf) {
+  float theta = u2 * 2.0f * 3.14f;
+  float rad = sqrtf(u);
+  float st, ct;
+  cr_sincos(theta, &st, &ct);
+  v3 local = mk3(rad * ct, rad * st, sqrtf(fmaxf(0.0f, 1.0f - u)));
+  const v3 zup = mk3(0.0f, 0.0f, 1.0f);
+  v3 l;
+  if (fabsf(dot(unit(n), zup)) == 1.0f) {
+    l = local * n.z;
+  } else {
+    l = unit(to_world(local, n, false));
+  }
+  *inv_pdf = 3.14f / fmaxf(dot(l, n), 0.0f);
+  return l;
+}
+
+// MathLib.cl:342-366
+RT_DEV v3 sample_uniform(v3 n, float u, float u2, float *inv_pdf) {
+  float phi = 2.0f * 3.14f * u;
+  float theta = cr_acos(1.0f - u2);
+  float st, ct, sp, cp;
+  cr_sincos(theta, &st, &ct);
+  cr_sincos(phi, &sp, &cp);
+  v3 local = mk3(cp * st, st * sp, ct);
+  *inv_pdf = 2.0f * 3.14f;
+  return to_world(local, n, true);
+}
+
+RT_DEV float ipow(float x, int n) {  // pown: repeated multiply from 1
+  float r = 1.0f;
+  for (int i = 0; i < n; ++i) r = r * x;
+  return r;
+}
+
+// MathLib.cl:461-500
+RT_DEV v3 bsdf_ggx(const Material &m, v3 v, v3 l, v3 n) {
+  v3 h = unit(l + v);
+  float a2 = ipow(m.roughness, 2);
+  float D = a2 / (3.14f * ipow(ipow(fmaxf(dot(n, h), 0.0f), 2) * (a2 - 1.0f) + 1.0f, 2));
+  float ndv = fmaxf(dot(n, v), 0.0f);
+  float kk = m.roughness * sqrtf(2.0f / 3.14f);
+  float g1 = ndv / (ndv * (1.0f - kk) + kk);
+  float ndl = fmaxf(dot(n, l), 0.0f);
+  float g2 = ndl / (ndl * (1.0f - kk) + kk);
+  float G = g1 * g2;
+  float F = 0.04f + (1.0f - 0.04f) * ipow(1.0f - fmaxf(dot(h, v), 0.0f), 5);
+  float spec = (F * G * D) * (1.0f / fmaxf(4.0f * fmaxf(dot(v, n), 0.0f) * fmaxf(dot(l, n), 0.0f), 0.001f));
+  float kd = (1.0f - F) * (1.0f - 0.5f);
+  v3 diffuse = (m.color * kd) / 3.14f;
+  return mk3(diffuse.x + spec, diffuse.y + spec, diffuse.z + spec);
+}
+
+}  // namespace b200rt

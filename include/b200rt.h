@@ -1,0 +1,155 @@
+/* b200rt — C ABI of the B200-native (sm_100a) path-tracing hot path.
+ *
+ * Drop-in boundary for the reference's KernelLauncher.py (QuentinHuan/ENSEM3A_OpenCLRaytracer):
+ * every entry point below replaces a piece of that file's PyOpenCL plumbing, cited as
+ * KernelLauncher.py:<line>.  Plain pointers and sizes only; all host buffers are owned by the
+ * caller and are only read (inputs) or written (outputs) during the call; all calls are
+ * synchronous unless the name ends in _device.  Every function returns 0 on success or a
+ * negative b200rt_status; b200rt_last_error() gives the message.  There is no CPU, OpenCL,
+ * OptiX or library fallback: without a usable CUDA device b200rt_create() fails.
+ *
+ * One context = one GPU = one host thread at a time.
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200rt_ctx b200rt_ctx;
+
+typedef enum {
+  B200RT_OK = 0,
+  B200RT_ERR_INVALID = -1,   /* bad argument / inconsistent buffers */
+  B200RT_ERR_CUDA = -2,      /* CUDA runtime error (message holds cudaGetErrorString) */
+  B200RT_ERR_NO_SCENE = -3,  /* render before b200rt_set_scene / b200rt_set_ibl */
+  B200RT_ERR_UNSUPPORTED = -4
+} b200rt_status;
+
+/* random-number modes */
+#define B200RT_RNG_REFERENCE 0 /* the reference's sequential per-pixel generator (MathLib.cl:294-310),
+                                  seeded with the pixel index as Raytracing.cl:171-172 does */
+#define B200RT_RNG_PHILOX 1    /* counter-based Philox4x32-10, counter = (pixel, sample, bounce, n), key = seed */
+
+/* traversal modes — both return the hit the reference's rayTrace (MathLib.cl:234-288) returns */
+#define B200RT_TRAVERSAL_FAST 0      /* front-to-back, distance-culled, ties resolved by the reference's visiting rank */
+#define B200RT_TRAVERSAL_REFERENCE 1 /* the reference's visiting order incl. its capped stack (stack.cl:21-26) */
+#define B200RT_TRAVERSAL_VERIFY 2    /* runs both per ray, counts disagreements in stats.mismatches, keeps REFERENCE */
+
+/* output modes */
+#define B200RT_OUT_FINAL 0 /* mean over spp, clamped to [0,1]  (Raytracing.cl:211-219) */
+#define B200RT_OUT_SUMS 1  /* raw per-pixel sums over [sample_begin, sample_end) — multi-GPU partials */
+
+typedef struct {
+  int32_t rng_mode;      /* B200RT_RNG_*           default REFERENCE */
+  int32_t traversal;     /* B200RT_TRAVERSAL_*     default FAST */
+  int32_t stack_cap;     /* REFERENCE traversal only; <=0 -> 20 (MathLib.cl:248); max 64 */
+  int32_t output;        /* B200RT_OUT_* */
+  int32_t sample_begin;  /* sample range [sample_begin, sample_end); end <= 0 -> [0, spp).            */
+  int32_t sample_end;    /*   a range not starting at 0 needs PHILOX (the reference stream is serial) */
+  int32_t pixel_begin;   /* work-item range [pixel_begin, pixel_end); end <= 0 -> [0, width*height)   */
+  int32_t pixel_end;
+  uint64_t seed;         /* Philox key */
+  int32_t collect_stats; /* 1: also count box / triangle tests (slower) */
+  int32_t reserved[5];
+} b200rt_opts;
+
+typedef struct {
+  uint64_t rays;        /* rayTrace invocations: primary + bounce + sun shadow rays */
+  uint64_t box_tests;   /* only with collect_stats */
+  uint64_t tri_tests;   /* only with collect_stats */
+  uint64_t mismatches;  /* TRAVERSAL_VERIFY only */
+  uint64_t samples;     /* pixel-samples evaluated */
+  float primary_ms;     /* device time of the primary-hit kernel (CUDA events) */
+  float trace_ms;       /* device time of the path-tracing kernel */
+  float total_ms;       /* first launch to last launch of the call, device time */
+  float upload_ms;      /* host->device copies of the call (wall clock) */
+  int32_t kernel_launches; /* kernels launched by the last call */
+  int32_t nodes;
+  int32_t triangles;
+  int32_t bvh_depth;
+  int32_t scene_in_smem;  /* 1 when the repacked scene is staged in shared memory */
+  int32_t reserved[3];
+} b200rt_stats;
+
+void b200rt_default_opts(b200rt_opts *opts);
+
+/* Context on CUDA device `device`.  Replaces cl.Context()/cl.CommandQueue()/Program.build()
+ * (main.py:21-28, KernelLauncher.py:8-31). */
+int b200rt_create(int device, b200rt_ctx **out_ctx);
+void b200rt_destroy(b200rt_ctx *ctx);
+const char *b200rt_last_error(const b200rt_ctx *ctx); /* ctx may be NULL: last create() error */
+
+/* Geometry, materials and BVH in the layouts FileManager.py/BVH.py emit; counts are
+ * array lengths in ELEMENTS.  Replaces the nine cl.Buffer(COPY_HOST_PTR) uploads,
+ * KernelLauncher.py:41-69.  light may be NULL/0 (the kernel never reads it).  Validates every index. */
+int b200rt_set_scene(b200rt_ctx *ctx, const float *vertex_p, int64_t n_vertex_p, const float *vertex_n,
+                     int64_t n_vertex_n, const float *vertex_uv, int64_t n_vertex_uv, const int32_t *face_data,
+                     int64_t n_face_data, const float *material_data, int64_t n_material_data,
+                     const int32_t *light_data, int64_t n_light_data, const float *bvh, int64_t n_bvh);
+
+/* Only the material table (6 floats per material) — the UI edits materials between renders. */
+int b200rt_set_materials(b200rt_ctx *ctx, const float *material_data, int64_t n_material_data);
+
+/* RGBA8 environment map, row-major, top row first.  Replaces cl.Image(...), KernelLauncher.py:71-72. */
+int b200rt_set_ibl(b200rt_ctx *ctx, const uint8_t *rgba, int width, int height);
+
+/* The `Raytracing` kernel + blocking read-back, KernelLauncher.py:76-78.  cam = 10 floats, env = 5
+ * floats (main.py:59-61,72-73).  width must equal (int)cam[6]; the frame has width*height work-items
+ * (height == width in the reference).  out_rgb: width*height*3 floats on the HOST. */
+int b200rt_render(b200rt_ctx *ctx, const float *cam, const float *env, int width, int height, int spp,
+                  int max_bounce, const b200rt_opts *opts, float *out_rgb);
+
+/* Same, but out_rgb is a DEVICE pointer on the context's GPU and the call returns after the kernels
+ * are enqueued on the context's stream (b200rt_sync waits).  Used by the multi-GPU path, whose
+ * per-GPU partial sums are reduced over NVLink before they ever reach the host. */
+int b200rt_render_device(b200rt_ctx *ctx, const float *cam, const float *env, int width, int height, int spp,
+                         int max_bounce, const b200rt_opts *opts, float *d_out_rgb);
+
+/* sums (B200RT_OUT_SUMS layout, device) -> clamp(sum / spp), device, in place allowed.  Raytracing.cl:211-219. */
+int b200rt_finalize_device(b200rt_ctx *ctx, const float *d_sums, float *d_out_rgb, int64_t n_pixels, int spp);
+
+/* Fused multi-GPU reduce + finalize: out = clamp((sum over n_parts partial-sum buffers) / spp).
+ * d_parts[] may be peer-GPU pointers mapped into this process (NVLink P2P loads). */
+int b200rt_reduce_finalize_device(b200rt_ctx *ctx, const float *const *d_parts, int n_parts, float *d_out_rgb,
+                                  int64_t n_pixels, int spp);
+
+int b200rt_sync(b200rt_ctx *ctx);
+
+/* Parity artefact: the primary ray's kept triangle (-1 = miss) and hit distance per work-item. */
+int b200rt_primary_hits(b200rt_ctx *ctx, const float *cam, int width, int height, const b200rt_opts *opts,
+                        int32_t *tri_out, float *k_out);
+
+/* Closest hit of n caller-supplied rays (6 floats each: origin, direction) — traversal on its own. */
+int b200rt_trace_rays(b200rt_ctx *ctx, const float *rays, int64_t n, const b200rt_opts *opts, int32_t *tri_out,
+                      float *k_out);
+
+/* The `ImgProcessing` kernel + read-back, KernelLauncher.py:90-103: dst[i] = powr(min(src[i],1), 2.2)
+ * for i < n, over `global` work-items (dst[i] untouched for n <= i < global). */
+int b200rt_img_processing(b200rt_ctx *ctx, const float *src, float *dst, int64_t n, int64_t global);
+
+int b200rt_get_stats(const b200rt_ctx *ctx, b200rt_stats *stats);
+
+/* Device math used by the kernels, exposed so tests can compare it value by value with the oracle:
+ * fn 0 sin, 1 cos, 2 acos, 3 asin, 4 atan2(a,b), 5 tan, 6 pow(a,b), 7 a/b through the traversal's
+ * reciprocal+FMA division, 8 sqrt. */
+int b200rt_math_probe(b200rt_ctx *ctx, int fn, const float *a, const float *b, int64_t n, float *out);
+
+/* Philox4x32-10 block of the device implementation (known-answer tests). */
+int b200rt_philox_probe(b200rt_ctx *ctx, const uint32_t ctr[4], uint32_t key0, uint32_t key1, uint32_t out[4]);
+
+/* CUDA IPC handle (64 bytes) of a device buffer owned by this context's process, and the reverse —
+ * lets one rank per GPU map its peers' partial-sum buffers for b200rt_reduce_finalize_device. */
+int b200rt_ipc_export(b200rt_ctx *ctx, const void *d_ptr, uint8_t handle_out[64]);
+int b200rt_ipc_open(b200rt_ctx *ctx, const uint8_t handle[64], void **d_ptr_out);
+int b200rt_ipc_close(b200rt_ctx *ctx, void *d_ptr);
+
+const char *b200rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H */
