@@ -44,8 +44,9 @@ class Stats(ctypes.Structure):
 SYMBOLS = [
     "b200rt_default_opts", "b200rt_create", "b200rt_destroy", "b200rt_last_error", "b200rt_set_scene",
     "b200rt_set_materials", "b200rt_set_ibl", "b200rt_render", "b200rt_render_device", "b200rt_finalize_device",
-    "b200rt_reduce_finalize_device", "b200rt_sync", "b200rt_primary_hits", "b200rt_trace_rays",
-    "b200rt_img_processing", "b200rt_get_stats", "b200rt_math_probe", "b200rt_philox_probe", "b200rt_ipc_export",
+    "b200rt_reduce_finalize_device", "b200rt_sync", "b200rt_set_stream", "b200rt_invalidate", "b200rt_primary_hits", "b200rt_trace_rays",
+    "b200rt_img_processing", "b200rt_get_stats", "b200rt_math_probe", "b200rt_philox_probe", "b200rt_alloc",
+    "b200rt_free", "b200rt_ipc_export",
     "b200rt_ipc_open", "b200rt_ipc_close", "b200rt_version",
 ]
 
@@ -84,12 +85,16 @@ def load_library():
     lib.b200rt_finalize_device.argtypes = [vp, vp, vp, i64, i32]
     lib.b200rt_reduce_finalize_device.argtypes = [vp, ctypes.POINTER(vp), i32, vp, i64, i32]
     lib.b200rt_sync.argtypes = [vp]
+    lib.b200rt_set_stream.argtypes = [vp, vp]
+    lib.b200rt_invalidate.argtypes = [vp]
     lib.b200rt_primary_hits.argtypes = [vp, vp, i32, i32, ctypes.POINTER(Opts), vp, vp]
     lib.b200rt_trace_rays.argtypes = [vp, vp, i64, ctypes.POINTER(Opts), vp, vp]
     lib.b200rt_img_processing.argtypes = [vp, vp, vp, i64, i64]
     lib.b200rt_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.b200rt_math_probe.argtypes = [vp, i32, vp, vp, i64, vp]
     lib.b200rt_philox_probe.argtypes = [vp, ctypes.POINTER(u32 * 4), u32, u32, ctypes.POINTER(u32 * 4)]
+    lib.b200rt_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
+    lib.b200rt_free.argtypes = [vp, vp]
     lib.b200rt_ipc_export.argtypes = [vp, vp, vp]
     lib.b200rt_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
     lib.b200rt_ipc_close.argtypes = [vp, vp]
@@ -213,6 +218,19 @@ class Context:
     def sync(self):
         self._check(self._lib.b200rt_sync(self._h), "b200rt_sync")
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: raw cudaStream_t as int (e.g. torch.cuda.current_stream().cuda_stream); None restores
+        the context's own stream.  0 (torch's default stream) is passed as cudaStreamLegacy (0x1), because a
+        NULL handle means "restore" in the C ABI."""
+        if cuda_stream is None:
+            h = None
+        else:
+            h = ctypes.c_void_p(int(cuda_stream) or 1)
+        self._check(self._lib.b200rt_set_stream(self._h, h), "b200rt_set_stream")
+
+    def invalidate(self):
+        self._check(self._lib.b200rt_invalidate(self._h), "b200rt_invalidate")
+
     def primary_hits(self, cam, width, height, opts=None):
         cam_ = _f32(cam)
         n = int(width) * int(height)
@@ -265,6 +283,14 @@ class Context:
         return np.array(list(o), dtype=np.uint32)
 
     # ---- CUDA IPC (multi-GPU peer reduce) -----------------------------------------------------------------------
+    def alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(self._lib.b200rt_alloc(self._h, int(nbytes), ctypes.byref(p)), "b200rt_alloc")
+        return p.value
+
+    def free(self, d_ptr):
+        self._check(self._lib.b200rt_free(self._h, ctypes.c_void_p(int(d_ptr))), "b200rt_free")
+
     def ipc_export(self, d_ptr):
         buf = (ctypes.c_uint8 * 64)()
         self._check(self._lib.b200rt_ipc_export(self._h, ctypes.c_void_p(int(d_ptr)), buf), "b200rt_ipc_export")

@@ -30,7 +30,8 @@ struct DevBuf {
 
 struct b200rt_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream in use
+  cudaStream_t own_stream = nullptr;  // created by b200rt_create
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   std::string err;
   int sm_count = 0;
@@ -38,6 +39,7 @@ struct b200rt_ctx {
 
   // scene
   bool have_scene = false;
+  bool have_scene_cached = false;  // scene_hash / ibl_hash are valid
   uint64_t scene_hash = 0, mat_hash = 0;
   DevBuf d_nodes, d_tris, d_normals, d_mats, d_bvh9;
   int n_nodes9 = 0, n_inner = 0, n_tris = 0, n_mats = 0;
@@ -218,38 +220,39 @@ int persistent_grid(b200rt_ctx *c, K kernel, size_t smem, int *grid) {
   return 0;
 }
 
-template <int TRAV, bool SMEM>
-int launch_primary_t(b200rt_ctx *c, const KernelArgs &A, bool parity, int *tri_out, float *k_out) {
+template <int TRAV, bool SMEM, bool PARITY, bool STATS>
+int launch_primary_t(b200rt_ctx *c, const KernelArgs &A, int *tri_out, float *k_out) {
+  auto k = k_primary<TRAV, SMEM, PARITY, STATS>;
   size_t smem = smem_bytes(c, SMEM);
   int grid = 0;
-  if (parity) {
-    auto k = k_primary<TRAV, SMEM, true>;
-    if (set_smem_attr(c, k, smem)) return B200RT_ERR_CUDA;
-    if (persistent_grid(c, k, smem, &grid)) return B200RT_ERR_CUDA;
-    int need = (A.n_work + kBlock - 1) / kBlock;
-    if (grid > need) grid = need;
-    k<<<grid, kBlock, smem, c->stream>>>(A, tri_out, k_out);
-  } else {
-    auto k = k_primary<TRAV, SMEM, false>;
-    if (set_smem_attr(c, k, smem)) return B200RT_ERR_CUDA;
-    if (persistent_grid(c, k, smem, &grid)) return B200RT_ERR_CUDA;
-    int need = (A.n_work + kBlock - 1) / kBlock;
-    if (grid > need) grid = need;
-    k<<<grid, kBlock, smem, c->stream>>>(A, tri_out, k_out);
-  }
+  if (set_smem_attr(c, k, smem)) return B200RT_ERR_CUDA;
+  if (persistent_grid(c, k, smem, &grid)) return B200RT_ERR_CUDA;
+  int need = (A.n_work + kBlock - 1) / kBlock;
+  if (grid > need) grid = need;
+  k<<<grid, kBlock, smem, c->stream>>>(A, tri_out, k_out);
   CU(cudaGetLastError());
   c->stats.kernel_launches++;
   return 0;
 }
 
-int launch_primary(b200rt_ctx *c, const KernelArgs &A, int trav, bool smem, bool parity, int *tri_out, float *k_out) {
+template <int TRAV, bool SMEM>
+int launch_primary_ts(b200rt_ctx *c, const KernelArgs &A, bool parity, bool stats, int *tri_out, float *k_out) {
+  if (TRAV == 2) stats = false;
+  if (parity) return stats ? launch_primary_t<TRAV, SMEM, true, (TRAV != 2)>(c, A, tri_out, k_out)
+                           : launch_primary_t<TRAV, SMEM, true, false>(c, A, tri_out, k_out);
+  return stats ? launch_primary_t<TRAV, SMEM, false, (TRAV != 2)>(c, A, tri_out, k_out)
+               : launch_primary_t<TRAV, SMEM, false, false>(c, A, tri_out, k_out);
+}
+
+int launch_primary(b200rt_ctx *c, const KernelArgs &A, int trav, bool smem, bool parity, bool stats, int *tri_out,
+                   float *k_out) {
   switch (trav * 2 + (smem ? 1 : 0)) {
-    case 0: return launch_primary_t<0, false>(c, A, parity, tri_out, k_out);
-    case 1: return launch_primary_t<0, true>(c, A, parity, tri_out, k_out);
-    case 2: return launch_primary_t<1, false>(c, A, parity, tri_out, k_out);
-    case 3: return launch_primary_t<1, true>(c, A, parity, tri_out, k_out);
-    case 4: return launch_primary_t<2, false>(c, A, parity, tri_out, k_out);
-    case 5: return launch_primary_t<2, true>(c, A, parity, tri_out, k_out);
+    case 0: return launch_primary_ts<0, false>(c, A, parity, stats, tri_out, k_out);
+    case 1: return launch_primary_ts<0, true>(c, A, parity, stats, tri_out, k_out);
+    case 2: return launch_primary_ts<1, false>(c, A, parity, stats, tri_out, k_out);
+    case 3: return launch_primary_ts<1, true>(c, A, parity, stats, tri_out, k_out);
+    case 4: return launch_primary_ts<2, false>(c, A, parity, stats, tri_out, k_out);
+    case 5: return launch_primary_ts<2, true>(c, A, parity, stats, tri_out, k_out);
   }
   return fail(c, B200RT_ERR_INVALID, "bad traversal mode %d", trav);
 }
@@ -373,7 +376,7 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   CU(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
   CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->stream));
   CU(cudaEventRecord(c->ev[0], c->stream));
-  rc = launch_primary(c, A, trav, smem, false, nullptr, nullptr);
+  rc = launch_primary(c, A, trav, smem, false, o.collect_stats != 0, nullptr, nullptr);
   if (rc) return rc;
   CU(cudaEventRecord(c->ev[1], c->stream));
   rc = launch_paths(c, A, trav, smem, o.collect_stats != 0);
@@ -429,7 +432,8 @@ int b200rt_create(int device, b200rt_ctx **out) {
     return B200RT_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
-  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  c->stream = c->own_stream;
   for (int i = 0; i < 3; ++i)
     if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&c->d_counters, sizeof(DeviceCounters))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -452,7 +456,7 @@ void b200rt_destroy(b200rt_ctx *c) {
   if (c->d_work) cudaFree(c->d_work);
   for (int i = 0; i < 3; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
 
@@ -469,7 +473,7 @@ int b200rt_set_materials(b200rt_ctx *c, const float *mat, int64_t n_mat) {
     if (m < 0 || m >= nm) return fail(c, B200RT_ERR_INVALID, "a triangle uses material %d but only %d materials were given", m, nm);
   CU(cudaSetDevice(c->device));
   uint64_t h = hash_bytes(mat, (size_t)n_mat * 4, 0x6d617473ull);
-  if (c->n_mats == nm && h == c->mat_hash && c->d_mats.p) return 0;
+  if (c->n_mats == nm && c->mat_hash != 0 && h == c->mat_hash && c->d_mats.p) return 0;
   if (ensure(c, c->d_mats, (size_t)n_mat * 4)) return B200RT_ERR_CUDA;
   CU(cudaMemcpyAsync(c->d_mats.p, mat, (size_t)n_mat * 4, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -497,7 +501,7 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   h = hash_bytes(vn, (size_t)n_vn * 4, h);
   h = hash_bytes(face, (size_t)n_face * 4, h);
   h = hash_bytes(bvh, (size_t)n_bvh * 4, h);
-  if (c->have_scene && h == c->scene_hash) {  // geometry unchanged (the UI rebuilds identical arrays per render, UI.py:98)
+  if (c->have_scene && c->have_scene_cached && h == c->scene_hash) {  // geometry unchanged (the UI rebuilds identical arrays per render, UI.py:98)
     int rc = b200rt_set_materials(c, mat, n_mat);
     c->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;
@@ -652,6 +656,7 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   int rc = b200rt_set_materials(c, mat, n_mat);
   if (rc) return rc;
   c->have_scene = true;
+  c->have_scene_cached = true;
   c->scene_hash = h;
   c->stats.nodes = n_nodes;
   c->stats.triangles = n_tris;
@@ -666,7 +671,7 @@ int b200rt_set_ibl(b200rt_ctx *c, const uint8_t *rgba, int width, int height) {
   if (width > 131072 || height > 65536) return fail(c, B200RT_ERR_UNSUPPORTED, "environment map %d x %d exceeds the 2-D texture limits", width, height);
   auto t0 = std::chrono::steady_clock::now();
   uint64_t h = hash_bytes(rgba, (size_t)width * height * 4, 0x69626cull);
-  if (c->have_ibl && h == c->ibl_hash && width == c->ibl_w && height == c->ibl_h) return 0;
+  if (c->have_ibl && c->ibl_hash != 0 && h == c->ibl_hash && width == c->ibl_w && height == c->ibl_h) return 0;
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   if (c->ibl_tex) { cudaDestroyTextureObject(c->ibl_tex); c->ibl_tex = 0; }
@@ -727,6 +732,24 @@ int b200rt_sync(b200rt_ctx *c) {
   return 0;
 }
 
+int b200rt_set_stream(b200rt_ctx *c, void *cuda_stream) {
+  if (!c) return B200RT_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->stats_pending) read_counters(c);
+  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return 0;
+}
+
+int b200rt_invalidate(b200rt_ctx *c) {
+  if (!c) return B200RT_ERR_INVALID;
+  c->scene_hash = 0;
+  c->mat_hash = 0;
+  c->ibl_hash = 0;
+  c->have_scene_cached = false;
+  return 0;
+}
+
 int b200rt_finalize_device(b200rt_ctx *c, const float *d_sums, float *d_out, int64_t n_pixels, int spp) {
   if (!c) return B200RT_ERR_INVALID;
   if (!d_sums || !d_out || n_pixels <= 0 || spp <= 0) return fail(c, B200RT_ERR_INVALID, "bad finalize arguments");
@@ -781,7 +804,7 @@ int b200rt_primary_hits(b200rt_ctx *c, const float *cam, int width, int height, 
   CU(cudaMemsetAsync(c->d_tmp_b.p, 0, npix * sizeof(float), c->stream));
   CU(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
   CU(cudaEventRecord(c->ev[0], c->stream));
-  rc = launch_primary(c, A, effective_traversal(c, o), use_smem_scene(c), true, static_cast<int *>(c->d_tmp_a.p),
+  rc = launch_primary(c, A, effective_traversal(c, o), use_smem_scene(c), true, o.collect_stats != 0, static_cast<int *>(c->d_tmp_a.p),
                       static_cast<float *>(c->d_tmp_b.p));
   if (rc) return rc;
   CU(cudaEventRecord(c->ev[1], c->stream));
@@ -892,6 +915,23 @@ int b200rt_philox_probe(b200rt_ctx *c, const uint32_t ctr[4], uint32_t key0, uin
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, c->d_misc.p, 16, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int b200rt_alloc(b200rt_ctx *c, int64_t bytes, void **d_ptr_out) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (bytes <= 0 || !d_ptr_out) return fail(c, B200RT_ERR_INVALID, "bad alloc arguments");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc(d_ptr_out, (size_t)bytes));
+  CU(cudaMemsetAsync(*d_ptr_out, 0, (size_t)bytes, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int b200rt_free(b200rt_ctx *c, void *d_ptr) {
+  if (!c) return B200RT_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaFree(d_ptr));
   return 0;
 }
 

@@ -102,15 +102,15 @@ RT_DEV void write_pixel(const KernelArgs &A, int i, v3 sum) {
     o[0] = sum.x; o[1] = sum.y; o[2] = sum.z;
   } else {  // Raytracing.cl:211-219
     float n = (float)A.F.spp;
-    o[0] = fmaxf(fminf(sum.x / n, 1.0f), 0.0f);
-    o[1] = fmaxf(fminf(sum.y / n, 1.0f), 0.0f);
-    o[2] = fmaxf(fminf(sum.z / n, 1.0f), 0.0f);
+    o[0] = clamp01(sum.x / n);
+    o[1] = clamp01(sum.y / n);
+    o[2] = clamp01(sum.z / n);
   }
 }
 
 // ---- primary hits ---------------------------------------------------------------------------------------
 // PARITY: write tri / k for every pixel of [pixel_begin,pixel_end) and nothing else.
-template <int TRAV, bool SMEM, bool PARITY>
+template <int TRAV, bool SMEM, bool PARITY, bool STATS>
 __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ KernelArgs A, int *tri_out, float *k_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   size_t used;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
     int i = work_to_pixel(A, w);
     if (i < 0) continue;
     v3 d = camera_dir(A.F, i);
-    Hit h = closest_hit<TRAV, SMEM, false>(S, A.F.cam_pos, d, st, &tc, &mism);
+    Hit h = closest_hit<TRAV, SMEM, STATS>(S, A.F.cam_pos, d, st, &tc, &mism);
     rays++;
     if (PARITY) {
       tri_out[i] = h.tri;
@@ -167,6 +167,10 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
   if ((threadIdx.x & 31) == 0) {
     if (rays) atomicAdd(&A.counters->rays, rays);
     if (mism) atomicAdd(&A.counters->mismatches, (unsigned long long)mism);
+  }
+  if (STATS) {
+    if (tc.box_tests) atomicAdd(&A.counters->box_tests, tc.box_tests);
+    if (tc.tri_tests) atomicAdd(&A.counters->tri_tests, tc.tri_tests);
   }
 }
 
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays(const __grid_constant__ K
 __global__ void k_finalize(const float *__restrict__ sums, float *__restrict__ out, long long n, float spp) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) out[i] = fmaxf(fminf(sums[i] / spp, 1.0f), 0.0f);
+  for (; i < n; i += stride) out[i] = clamp01(sums[i] / spp);
 }
 
 // fused multi-GPU reduce + finalize: parts[] may live on peer GPUs (NVLink P2P loads); summed in rank order
@@ -404,16 +408,16 @@ __global__ void k_reduce_finalize(const __grid_constant__ PartList parts, float 
       float4 b = reinterpret_cast<const float4 *>(parts.p[r])[v];
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    a.x = fmaxf(fminf(a.x / spp, 1.0f), 0.0f);
-    a.y = fmaxf(fminf(a.y / spp, 1.0f), 0.0f);
-    a.z = fmaxf(fminf(a.z / spp, 1.0f), 0.0f);
-    a.w = fmaxf(fminf(a.w / spp, 1.0f), 0.0f);
+    a.x = clamp01(a.x / spp);
+    a.y = clamp01(a.y / spp);
+    a.z = clamp01(a.z / spp);
+    a.w = clamp01(a.w / spp);
     reinterpret_cast<float4 *>(out)[v] = a;
   }
   for (long long e = 4 * n4 + i; e < n; e += stride) {
     float a = parts.p[0][e];
     for (int r = 1; r < parts.n; ++r) a += parts.p[r][e];
-    out[e] = fmaxf(fminf(a / spp, 1.0f), 0.0f);
+    out[e] = clamp01(a / spp);
   }
 }
 

@@ -41,6 +41,14 @@ RT_HD v3 cross(v3 a, v3 b) {
 }
 RT_HD v3 unit(v3 a) { return a / sqrtf(dot(a, a)); }
 
+// fmax(fmin(x, 1), 0) with OpenCL/IEEE minNum semantics (Raytracing.cl:217-219): a NaN becomes 1, not 0.
+// nvcc fuses the plain fmaxf(fminf(x,1),0) into FADD.SAT, whose NaN result is +0, so NaN is handled
+// explicitly (tests/test_gpu_parity.py::test_nan_and_inf_semantics_survive).
+RT_DEV float clamp01(float x) {
+  float t = fmaxf(fminf(x, 1.0f), 0.0f);
+  return (x != x) ? 1.0f : t;
+}
+
 // ---- correctly-rounded binary32 transcendentals (binary64 evaluation, one rounding) ----
 RT_DEV float cr_sin(float a) { return __double2float_rn(sin((double)a)); }
 RT_DEV float cr_cos(float a) { return __double2float_rn(cos((double)a)); }
@@ -127,7 +135,11 @@ RT_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 
 // Two uniform draws for bounce `j` of sample `s` of pixel `i`.
 struct rng_state {
-  uint32_t a;  // reference generator: the kernel's seed0 word (its seed1 is write-only, see rt_oracle.c)
+  // Reference generator (MathLib.cl:294-310) as the kernel wires it: Raytracing.cl:205-206 passes
+  // (&seed0,&seed1), naiveGI swaps them for the samplers (:61-69), so on the kernel's own words
+  // seed1 <- 36969*(seed0&65535)+(seed0>>16); seed0 <- 18000*(seed1&65535)+(seed1>>16); bits = (seed1<<16)+seed0.
+  // The incoming seed1 is never read: the whole state is seed0.
+  uint32_t a;
 };
 
 template <int RNG>

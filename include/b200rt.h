@@ -119,6 +119,15 @@ int b200rt_reduce_finalize_device(b200rt_ctx *ctx, const float *const *d_parts, 
 
 int b200rt_sync(b200rt_ctx *ctx);
 
+/* Run this context's kernels and copies on a caller-owned CUDA stream (cudaStream_t passed as void*),
+ * e.g. the stream a torch.distributed / NCCL collective is enqueued on; NULL restores the context's own. */
+int b200rt_set_stream(b200rt_ctx *ctx, void *cuda_stream);
+
+/* Forget the content hashes of the cached scene / environment uploads: the next b200rt_set_scene and
+ * b200rt_set_ibl copy host->device again even if the bytes are unchanged (what the reference does on
+ * every render, KernelLauncher.py:38-72). */
+int b200rt_invalidate(b200rt_ctx *ctx);
+
 /* Parity artefact: the primary ray's kept triangle (-1 = miss) and hit distance per work-item. */
 int b200rt_primary_hits(b200rt_ctx *ctx, const float *cam, int width, int height, const b200rt_opts *opts,
                         int32_t *tri_out, float *k_out);
@@ -140,6 +149,12 @@ int b200rt_math_probe(b200rt_ctx *ctx, int fn, const float *a, const float *b, i
 
 /* Philox4x32-10 block of the device implementation (known-answer tests). */
 int b200rt_philox_probe(b200rt_ctx *ctx, const uint32_t ctr[4], uint32_t key0, uint32_t key1, uint32_t out[4]);
+
+/* Plain cudaMalloc / cudaFree on the context's GPU (zero-initialised).  Buffers that are exported with
+ * b200rt_ipc_export must come from here: an IPC handle names a whole allocation, so a sub-range of a
+ * framework's caching allocator cannot be shared. */
+int b200rt_alloc(b200rt_ctx *ctx, int64_t bytes, void **d_ptr_out);
+int b200rt_free(b200rt_ctx *ctx, void *d_ptr);
 
 /* CUDA IPC handle (64 bytes) of a device buffer owned by this context's process, and the reverse —
  * lets one rank per GPU map its peers' partial-sum buffers for b200rt_reduce_finalize_device. */

@@ -1,0 +1,184 @@
+"""GPU: the drop-in KernelLauncher (reference KernelLauncher.py call surface) and full-size properties at the
+BASELINE.json configurations."""
+import numpy as np
+import pytest
+
+import ensem3a_openclraytracer_b200 as rt
+from oracle import oracle
+from tests import fixtures
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+class FakePILImage:
+    """What main.py:68-69 hands over: an object with .size == (W, H) and .tobytes() (KernelLauncher.py:72)."""
+
+    def __init__(self, rgba):
+        self._a = np.ascontiguousarray(rgba)
+        self.size = (self._a.shape[1], self._a.shape[0])
+
+    def tobytes(self):
+        return self._a.tobytes()
+
+
+@pytest.fixture(scope="module")
+def launcher():
+    kl = rt.KernelLauncher("context", "platform", "device", "queue")  # OpenCL objects are accepted and ignored
+    yield kl
+    kl.close()
+
+
+def test_launch_raytracing_config1_exact(launcher):
+    """BASELINE config 1 = the reference's own CPU-runnable case: Cornell box 512x512, 16 spp, maxBounce 4."""
+    sc = fixtures.load_scene("cornell")
+    ibl = fixtures.load_ibl()
+    res, spp = 512, 16
+    cam, env = fixtures.cam_env(sc["params"], res)
+    out = np.zeros(res * res * 3, np.float32)
+    ret = launcher.launch_Raytracing(out, sc["V_p"], sc["V_n"], sc["V_uv"], sc["faceData"], sc["materialData"],
+                                     sc["lightData"], sc["BVH"], cam, env, res * res, spp, 4, FakePILImage(ibl))
+    assert ret is None
+    assert launcher.last_stats["rays"] == 15235215          # the oracle's ray count for config 1
+    # a band of rows against the oracle (the whole frame takes the CPU ~10 s)
+    i0, i1 = 200 * res, 232 * res
+    want, _ = oracle.render(sc, cam, env, res * res, spp, 4, ibl, i0=i0, i1=i1)
+    assert np.array_equal(bits(out[3 * i0:3 * i1]), bits(want[3 * i0:3 * i1]))
+    img = out.reshape(res, res, 3)
+    assert np.array_equal(img[0, :-1], img[1, :-1])          # the reference's duplicated first row
+    assert out.min() >= 0.0 and out.max() <= 1.0
+
+
+def test_launcher_accepts_reference_style_inputs(launcher):
+    """float64 cam like np.array([...]) before .astype, int64 light list, list inputs, empty light list."""
+    sc = fixtures.load_scene("proto")
+    ibl = fixtures.load_ibl()
+    res = 64
+    cam, env = fixtures.cam_env(sc["params"], res)
+    want, _ = oracle.render(sc, cam, env, res * res, 3, 4, ibl)
+    out = np.zeros(res * res * 3, np.float32)
+    launcher.launch_Raytracing(out, sc["V_p"].astype(np.float64), list(sc["V_n"]), sc["V_uv"], sc["faceData"].astype(np.int64),
+                               sc["materialData"], np.array([], dtype=np.int64), sc["BVH"], cam.astype(np.float64),
+                               env.astype(np.float64), res * res, 3, 4, ibl)
+    assert np.array_equal(bits(out), bits(want))
+
+
+def test_launcher_rejects_bad_inputs(launcher):
+    sc = fixtures.load_scene("cornell")
+    ibl = fixtures.load_ibl()
+    cam, env = fixtures.cam_env(sc["params"], 16)
+    good = [sc["V_p"], sc["V_n"], sc["V_uv"], sc["faceData"], sc["materialData"], sc["lightData"], sc["BVH"]]
+    out = np.zeros(16 * 16 * 3, np.float32)
+    with pytest.raises(ValueError):
+        launcher.launch_Raytracing(out, *good, cam, env, 16 * 16 + 3, 1, 1, ibl)       # not whole rows
+    with pytest.raises(ValueError):
+        launcher.launch_Raytracing(out[:10], *good, cam, env, 16 * 16, 1, 1, ibl)      # output too small
+    with pytest.raises(TypeError):
+        launcher.launch_Raytracing(out.astype(np.float64), *good, cam, env, 16 * 16, 1, 1, ibl)
+    bad_face = sc["faceData"].copy()
+    bad_face[7] = 10 ** 6                                                               # position index out of range
+    with pytest.raises(rt.B200RTError, match="out of range"):
+        launcher.launch_Raytracing(out, sc["V_p"], sc["V_n"], sc["V_uv"], bad_face, sc["materialData"], sc["lightData"],
+                                   sc["BVH"], cam, env, 16 * 16, 1, 1, ibl)
+    bad_bvh = sc["BVH"].copy()
+    bad_bvh[0] = 0.0                                                                    # root is its own left child
+    with pytest.raises(rt.B200RTError, match="not a tree"):
+        launcher.launch_Raytracing(out, sc["V_p"], sc["V_n"], sc["V_uv"], sc["faceData"], sc["materialData"], sc["lightData"],
+                                   bad_bvh, cam, env, 16 * 16, 1, 1, ibl)
+    bad_mat = sc["materialData"].copy()
+    bad_mat[0] = 7.0
+    with pytest.raises(rt.B200RTError, match="types 0..3"):
+        launcher.launch_Raytracing(out, sc["V_p"], sc["V_n"], sc["V_uv"], sc["faceData"], bad_mat, sc["lightData"], sc["BVH"],
+                                   cam, env, 16 * 16, 1, 1, ibl)
+    with pytest.raises(rt.B200RTError):
+        launcher.launch_Raytracing(out, *good, cam, env, 16 * 16, 0, 1, ibl)           # spp = 0
+
+
+def test_material_edit_between_renders(launcher):
+    """The UI edits the .ini and re-renders with identical geometry (UI.py:92-104): geometry upload is cached, the new
+    materials must still take effect."""
+    sc = fixtures.load_scene("cornell")
+    ibl = fixtures.load_ibl()
+    res = 48
+    cam, env = fixtures.cam_env(sc["params"], res)
+    args = lambda m: (sc["V_p"], sc["V_n"], sc["V_uv"], sc["faceData"], m, sc["lightData"], sc["BVH"], cam, env, res * res, 4, 4, ibl)
+    a = np.zeros(res * res * 3, np.float32)
+    launcher.launch_Raytracing(a, *args(sc["materialData"]))
+    m2 = sc["materialData"].copy()
+    m2[6 * 3 + 4] = 8.0            # give the lamp (material 3, type 0) an emissive power
+    m2[6 * 1 + 0] = 2.0            # red wall becomes glossy
+    m2[6 * 1 + 4] = 0.3
+    b = np.zeros_like(a)
+    launcher.launch_Raytracing(b, *args(m2))
+    want, _ = oracle.render(dict(sc, materialData=m2), cam, env, res * res, 4, 4, ibl)
+    assert np.array_equal(bits(b), bits(want))
+    assert not np.array_equal(a, b)
+
+
+def test_launch_img_processing(launcher):
+    src = np.random.default_rng(0).uniform(0, 1.4, 64 * 64 * 3).astype(np.float32)
+    out = np.zeros_like(src)
+    assert launcher.launch_ImgProcessing(src, out, 64) is None
+    assert np.array_equal(bits(out), bits(oracle.img_processing(src, 64 * 64 * 3)))
+
+
+# ---- full-size properties (BASELINE configs 2-4 at their real frame sizes, reduced spp) ---------------------------------
+def test_1080p_determinism_and_traversal_equivalence(gpu_ctx):
+    sc = fixtures.load_scene("monkey_cfg2")
+    fixtures.upload(gpu_ctx, sc)
+    W, H = 1920, 1080
+    cam, env = fixtures.cam_env(sc["params"], W, H)
+    o = lambda **kw: rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=0, **kw)
+    a = gpu_ctx.render(cam, env, W, H, 4, 4, opts=o())
+    rays = gpu_ctx.stats()["rays"]
+    b = gpu_ctx.render(cam, env, W, H, 4, 4, opts=o())
+    assert np.array_equal(bits(a), bits(b)), "two runs with the same seed differ"
+    c = gpu_ctx.render(cam, env, W, H, 4, 4, opts=o(traversal=rt.TRAVERSAL_REFERENCE))
+    assert gpu_ctx.stats()["rays"] == rays
+    assert np.array_equal(bits(a), bits(c)), "fast and reference traversal render different 1080p frames"
+    # a band of the frame against the oracle
+    i0, i1 = 500 * W, 506 * W
+    want, _ = oracle.render(sc, cam, env, W * H, 4, 4, fixtures.load_ibl(), i0=i0, i1=i1, rng_mode=oracle.RNG_PHILOX, seed=0)
+    assert np.array_equal(bits(a[3 * i0:3 * i1]), bits(want[3 * i0:3 * i1]))
+
+
+def test_1080p_verify_mode_reference_rng(gpu_ctx):
+    """Every ray of a 1080p Cornell frame through both traversals: zero disagreements."""
+    sc = fixtures.load_scene("cornell")
+    fixtures.upload(gpu_ctx, sc)
+    W, H = 1920, 1080
+    cam, env = fixtures.cam_env(sc["params"], W, H)
+    gpu_ctx.render(cam, env, W, H, 4, 4, opts=rt.make_opts(traversal=rt.TRAVERSAL_VERIFY))
+    st = gpu_ctx.stats()
+    assert st["rays"] > 2 * W * H and st["mismatches"] == 0
+
+
+def test_furnace_energy_matches_oracle(gpu_ctx):
+    """BASELINE config 3: furnace under a uniform environment — the check is 'same mean radiance as the oracle',
+    not '= 1': the reference BSDF is not energy-conserving."""
+    sc = fixtures.load_scene("furnace_cfg3")
+    grey = fixtures.load_ibl("grey")
+    fixtures.upload(gpu_ctx, sc, grey)
+    res = 256
+    cam, env = fixtures.cam_env(sc["params"], res)
+    out = gpu_ctx.render(cam, env, res, res, 16, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=2))
+    want, _ = oracle.render(sc, cam, env, res * res, 16, 4, grey, rng_mode=oracle.RNG_PHILOX, seed=2)
+    assert np.array_equal(bits(out), bits(want))
+    assert abs(float(out.mean()) - float(want.mean())) < 1e-7
+
+
+def test_4k_frame_runs_and_tiles(gpu_ctx):
+    """BASELINE config 4 frame size (3840x2160, Serre): pixel-range halves tile the frame bit-exactly."""
+    sc = fixtures.load_scene("serre")
+    fixtures.upload(gpu_ctx, sc)
+    W, H = 3840, 2160
+    cam, env = fixtures.cam_env(sc["params"], W, H)
+    mk = lambda **kw: rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=1, output=rt.OUT_SUMS, **kw)
+    full = gpu_ctx.render(cam, env, W, H, 2, 4, opts=mk())
+    half = (H // 2) * W
+    top = gpu_ctx.render(cam, env, W, H, 2, 4, opts=mk(pixel_begin=0, pixel_end=half))
+    bot = gpu_ctx.render(cam, env, W, H, 2, 4, opts=mk(pixel_begin=half, pixel_end=W * H))
+    assert np.array_equal(bits(top + bot), bits(full))

@@ -1,0 +1,302 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle, the committed golden
+vectors and, at BASELINE.json's full sizes, size-independent properties.
+
+Bars (north_star): primary-ray triangle ids and hit distances BIT-EXACT; per-pixel radiance at fixed
+seeds within 1e-4 relative (REL_TOL below; in practice every pixel is bit-identical, which the tests also
+record through IDENTICAL_MIN).
+"""
+import numpy as np
+import pytest
+
+import ensem3a_openclraytracer_b200 as rt
+from oracle import oracle
+from tests import fixtures
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4          # north_star: per-pixel radiance within 1e-4 relative at fixed seeds
+REL_FLOOR = 1e-3        # denominators below this are treated as absolute differences
+IDENTICAL_MIN = 0.999   # fraction of pixels expected bit-identical (measured: 1.0 everywhere)
+
+VARIANTS = ["cornell", "monkey", "monkey_cfg2", "furnace", "furnace_cfg3", "serre", "proto", "single"]
+TRAVERSALS = [rt.TRAVERSAL_FAST, rt.TRAVERSAL_REFERENCE]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_radiance(out, ref):
+    rel = np.abs(out - ref) / np.maximum(np.abs(ref), REL_FLOOR)
+    assert np.nanmax(rel) <= REL_TOL, f"max relative error {np.nanmax(rel)}"
+    assert np.mean(bits(out) == bits(ref)) >= IDENTICAL_MIN
+
+
+def ibl_for(name):
+    return fixtures.load_ibl("grey" if name == "furnace_cfg3" else "preview")
+
+
+# ---- device arithmetic -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fn,code,lo,hi", [("sin", 0, -7, 7), ("cos", 1, -7, 7), ("acos", 2, -1, 1), ("asin", 3, -1, 1),
+                                          ("tan", 5, -1.5, 1.5), ("sin", 9, -7, 7), ("cos", 10, -7, 7)])
+def test_transcendentals_are_correctly_rounded(gpu_ctx, fn, code, lo, hi):
+    a = np.random.default_rng(code).uniform(lo, hi, 1 << 21).astype(np.float32)
+    a[:8] = [0.0, -0.0, lo, hi, 1e-30, -1e-30, 0.5, 1.0] if fn not in ("acos", "asin") else [0, -0.0, -1, 1, 1e-30, -1e-30, 0.5, 0.99999994]
+    assert np.array_equal(bits(gpu_ctx.math_probe(code, a)), bits(oracle.math_probe(fn, a)))
+
+
+def test_atan2_pow_sqrt(gpu_ctx):
+    r = np.random.default_rng(1)
+    a, b = r.uniform(-1, 1, 1 << 20).astype(np.float32), r.uniform(-1, 1, 1 << 20).astype(np.float32)
+    assert np.array_equal(bits(gpu_ctx.math_probe(4, a, b)), bits(oracle.math_probe("atan2", a, b)))
+    x = r.uniform(0, 1.0, 1 << 20).astype(np.float32)
+    g = np.full_like(x, 2.2)
+    assert np.array_equal(bits(gpu_ctx.math_probe(6, x, g)), bits(oracle.math_probe("pow", x, g)))
+    x = (r.uniform(0, 1, 1 << 20) * 10.0 ** r.uniform(-20, 20, 1 << 20)).astype(np.float32)
+    assert np.array_equal(bits(gpu_ctx.math_probe(8, x)), bits(np.sqrt(x)))
+
+
+def test_reciprocal_fma_division_is_ieee_division(gpu_ctx):
+    """div_by(): x * RN(1/d) + two FMA corrections must equal IEEE x / d for every operand the slab test
+    can see (|d| in [2^-40, 2^40]; outside that range the kernel uses true division anyway)."""
+    r = np.random.default_rng(2)
+    n = 1 << 22
+    a = (r.standard_normal(n) * 10.0 ** r.uniform(-8, 8, n)).astype(np.float32)
+    b = (r.standard_normal(n) * 10.0 ** r.uniform(-11, 11, n)).astype(np.float32)
+    a[:6] = [0.0, -0.0, 1.0, -1.0, 3.0, 16777215.0]
+    b[:6] = [3.0, 7.0, 3.0, 3.0, 0.0, 16777213.0]
+    got = gpu_ctx.math_probe(7, a, b)
+    with np.errstate(all="ignore"):
+        want = (a / b).astype(np.float32)
+    same = (bits(got) == bits(want)) | ((got == 0) & (want == 0)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), f"{(~same).sum()} quotients differ"
+    # adversarial mantissas: numerators/denominators near powers of two and all-ones patterns
+    m = np.array([0x3f800000, 0x3f800001, 0x3fffffff, 0x3f7fffff, 0x40000001, 0x3fc00000, 0x3faaaaab, 0x3f000001],
+                 dtype=np.uint32).view(np.float32)
+    a2, b2 = np.meshgrid(m, m)
+    got = gpu_ctx.math_probe(7, a2.ravel(), b2.ravel())
+    assert np.array_equal(bits(got), bits((a2.ravel() / b2.ravel()).astype(np.float32)))
+
+
+def test_philox_known_answers(gpu_ctx):
+    for ctr, k0, k1, want in [
+        ([0, 0, 0, 0], 0, 0, [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, 0xffffffff, 0xffffffff, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], 0xa4093822, 0x299f31d0,
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]:
+        assert [int(v) for v in gpu_ctx.philox_probe(ctr, k0, k1)] == want
+
+
+# ---- primary hits: bit-exact ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("trav", TRAVERSALS)
+@pytest.mark.parametrize("name", VARIANTS)
+def test_primary_hits_golden(gpu_ctx, name, trav):
+    g = fixtures.golden()
+    sc = fixtures.load_scene(name)
+    fixtures.upload(gpu_ctx, sc)
+    cam, _ = fixtures.cam_env(sc["params"], 128)
+    tri, k = gpu_ctx.primary_hits(cam, 128, 128, rt.make_opts(traversal=trav))
+    assert np.array_equal(tri, g[f"{name}/primary_tri"])
+    assert np.array_equal(bits(k), bits(g[f"{name}/primary_k"]))
+
+
+@pytest.mark.parametrize("name,res", [("cornell", 512), ("monkey", 400), ("serre", 320), ("furnace", 384), ("proto", 384)])
+def test_primary_hits_oracle_large(gpu_ctx, name, res):
+    sc = fixtures.load_scene(name)
+    fixtures.upload(gpu_ctx, sc)
+    cam, _ = fixtures.cam_env(sc["params"], res)
+    want = oracle.primary(sc, cam, res * res)
+    tri, k = gpu_ctx.primary_hits(cam, res, res)
+    assert np.array_equal(tri, want["tri"])
+    assert np.array_equal(bits(k), bits(want["k"]))
+
+
+def test_primary_hits_non_square_golden(gpu_ctx):
+    g = fixtures.golden()
+    sc = fixtures.load_scene("cornell")
+    fixtures.upload(gpu_ctx, sc)
+    tri, k = gpu_ctx.primary_hits(g["cornell_96x54/cam"], 96, 54)
+    assert np.array_equal(tri, g["cornell_96x54/primary_tri"])
+    assert np.array_equal(bits(k), bits(g["cornell_96x54/primary_k"]))
+
+
+def test_arbitrary_rays_all_traversals(gpu_ctx):
+    """Closest hit of random rays (inside, outside, axis-aligned, zero components, degenerate)."""
+    sc = fixtures.load_scene("serre")
+    fixtures.upload(gpu_ctx, sc)
+    r = np.random.default_rng(5)
+    n = 60000
+    rays = np.zeros((n, 6), np.float32)
+    rays[:, :3] = r.uniform(-12, 12, (n, 3))
+    rays[:, 3:] = r.standard_normal((n, 3))
+    rays[:2000, 3] = 0.0                      # direction with an exactly-zero component (division by zero)
+    rays[2000:3000, 3:5] = 0.0
+    rays[3000:3200, 3:] = 0.0                 # null direction: 0/0 everywhere
+    rays[3200:3400, 3:] *= 1e-20
+    rays[3400:3600, :3] *= 1e6
+    rays[3600:3700, 3] = np.nan
+    want_tri, want_k, cnt = oracle.trace_rays(sc, rays)
+    for trav in (rt.TRAVERSAL_FAST, rt.TRAVERSAL_REFERENCE, rt.TRAVERSAL_VERIFY):
+        tri, k = gpu_ctx.trace_rays(rays, rt.make_opts(traversal=trav))
+        assert np.array_equal(tri, want_tri), f"traversal {trav}: {(tri != want_tri).sum()} triangle ids differ"
+        assert np.array_equal(bits(k), bits(want_k))
+        if trav == rt.TRAVERSAL_VERIFY:
+            assert gpu_ctx.stats()["mismatches"] == 0
+    # the reference traversal counts exactly the oracle's box / triangle tests
+    gpu_ctx.trace_rays(rays, rt.make_opts(traversal=rt.TRAVERSAL_REFERENCE, collect_stats=True))
+    st = gpu_ctx.stats()
+    assert (st["box_tests"], st["tri_tests"]) == (cnt["box_tests"], cnt["tri_tests"])
+
+
+def test_capped_stack_compat_switch(gpu_ctx):
+    """REFERENCE traversal with the reference's capped stack drops the same pushes the oracle drops."""
+    sc = fixtures.load_scene("proto")
+    fixtures.upload(gpu_ctx, sc)
+    cam, _ = fixtures.cam_env(sc["params"], 96)
+    for cap in (3, 5, 20):
+        want = oracle.primary(sc, cam, 96 * 96, stack_cap=cap)
+        tri, k = gpu_ctx.primary_hits(cam, 96, 96, rt.make_opts(traversal=rt.TRAVERSAL_REFERENCE, stack_cap=cap))
+        assert np.array_equal(tri, want["tri"]) and np.array_equal(bits(k), bits(want["k"]))
+
+
+# ---- rendered pixels ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("trav", TRAVERSALS)
+@pytest.mark.parametrize("name", VARIANTS)
+def test_render_golden(gpu_ctx, name, trav):
+    g = fixtures.golden()
+    sc = fixtures.load_scene(name)
+    fixtures.upload(gpu_ctx, sc, ibl_for(name))
+    out = gpu_ctx.render(g[f"{name}/cam"], g[f"{name}/env"], 64, 64, 8, 4, opts=rt.make_opts(traversal=trav, collect_stats=True))
+    assert_radiance(out, g[f"{name}/render"])
+    st = gpu_ctx.stats()
+    rays, box, tri, _ = [int(x) for x in g[f"{name}/counters"]]
+    assert st["rays"] == rays
+    if trav == rt.TRAVERSAL_REFERENCE:
+        assert (st["box_tests"], st["tri_tests"]) == (box, tri)
+    else:
+        assert st["box_tests"] <= box and st["tri_tests"] <= tri
+
+
+def test_render_non_square_and_rotated_golden(gpu_ctx):
+    g = fixtures.golden()
+    sc = fixtures.load_scene("cornell")
+    fixtures.upload(gpu_ctx, sc)
+    out = gpu_ctx.render(g["cornell_96x54/cam"], g["cornell_96x54/env"], 96, 54, 4, 4)
+    assert_radiance(out, g["cornell_96x54/render"])
+    sc = fixtures.load_scene("serre")
+    fixtures.upload(gpu_ctx, sc)
+    out = gpu_ctx.render(g["serre_rot/cam"], g["serre_rot/env"], 48, 48, 6, 2)
+    assert_radiance(out, g["serre_rot/render"])
+
+
+@pytest.mark.parametrize("name,res,spp,bounce,rng", [
+    ("cornell", 160, 12, 4, rt.RNG_REFERENCE), ("cornell", 160, 12, 4, rt.RNG_PHILOX), ("monkey_cfg2", 96, 6, 4, rt.RNG_PHILOX),
+    ("serre", 96, 6, 3, rt.RNG_PHILOX), ("furnace_cfg3", 96, 8, 4, rt.RNG_PHILOX), ("proto", 97, 5, 0, rt.RNG_REFERENCE),
+    ("single", 33, 3, 2, rt.RNG_PHILOX)])
+def test_render_oracle(gpu_ctx, name, res, spp, bounce, rng):
+    sc = fixtures.load_scene(name)
+    ibl = ibl_for(name)
+    fixtures.upload(gpu_ctx, sc, ibl)
+    cam, env = fixtures.cam_env(sc["params"], res)
+    want, cnt = oracle.render(sc, cam, env, res * res, spp, bounce, ibl, rng_mode=rng, seed=1234567890123)
+    out = gpu_ctx.render(cam, env, res, res, spp, bounce, opts=rt.make_opts(rng_mode=rng, seed=1234567890123))
+    assert_radiance(out, want)
+    assert gpu_ctx.stats()["rays"] == cnt["rays"]
+
+
+def test_verify_mode_finds_no_disagreement(gpu_ctx):
+    for name in ("cornell", "monkey_cfg2", "serre"):
+        sc = fixtures.load_scene(name)
+        fixtures.upload(gpu_ctx, sc)
+        cam, env = fixtures.cam_env(sc["params"], 200)
+        gpu_ctx.render(cam, env, 200, 200, 8, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, traversal=rt.TRAVERSAL_VERIFY))
+        st = gpu_ctx.stats()
+        assert st["mismatches"] == 0, f"{name}: fast and reference traversal disagree on {st['mismatches']} of {st['rays']} rays"
+
+
+def test_sample_and_pixel_ranges(gpu_ctx):
+    """OUT_SUMS partials: sample ranges add up to the full sum; pixel ranges tile the frame bit-exactly."""
+    sc = fixtures.load_scene("cornell")
+    ibl = fixtures.load_ibl()
+    fixtures.upload(gpu_ctx, sc, ibl)
+    W, H, spp = 72, 40, 10
+    cam, env = fixtures.cam_env(sc["params"], W, H)
+    mk = lambda **kw: rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=4, output=rt.OUT_SUMS, **kw)
+    full = gpu_ctx.render(cam, env, W, H, spp, 4, opts=mk())
+    want, _ = oracle.render(sc, cam, env, W * H, spp, 4, ibl, rng_mode=oracle.RNG_PHILOX, seed=4, raw_sums=True)
+    assert np.array_equal(bits(full), bits(want))
+    a = gpu_ctx.render(cam, env, W, H, spp, 4, opts=mk(sample_begin=0, sample_end=3))
+    b = gpu_ctx.render(cam, env, W, H, spp, 4, opts=mk(sample_begin=3, sample_end=10))
+    wa, _ = oracle.render(sc, cam, env, W * H, spp, 4, ibl, rng_mode=oracle.RNG_PHILOX, seed=4, raw_sums=True, s0=0, s1=3)
+    assert np.array_equal(bits(a), bits(wa))
+    np.testing.assert_allclose(a + b, full, rtol=1e-5, atol=1e-6)
+    top = gpu_ctx.render(cam, env, W, H, spp, 4, opts=mk(pixel_begin=0, pixel_end=16 * W))
+    bot = gpu_ctx.render(cam, env, W, H, spp, 4, opts=mk(pixel_begin=16 * W, pixel_end=W * H))
+    assert np.all(top[16 * W * 3:] == 0) and np.all(bot[:16 * W * 3] == 0)
+    assert np.array_equal(bits(top + bot), bits(full))
+
+
+def test_edge_cases(gpu_ctx):
+    sc = fixtures.load_scene("cornell")
+    ibl = fixtures.load_ibl()
+    fixtures.upload(gpu_ctx, sc, ibl)
+    for W, H, spp, mb in [(1, 1, 1, 0), (7, 3, 2, 1), (9, 5, 1, 4), (8, 4, 3, 0), (33, 1, 2, 2)]:
+        cam, env = fixtures.cam_env(sc["params"], W, H)
+        want, _ = oracle.render(sc, cam, env, W * H, spp, mb, ibl)
+        out = gpu_ctx.render(cam, env, W, H, spp, mb)
+        assert np.array_equal(bits(out), bits(want)), (W, H, spp, mb)
+    # 1x1 environment map, empty light list, IBL power on
+    one = np.array([[[10, 200, 30, 255]]], np.uint8)
+    sc2 = dict(sc, lightData=np.zeros(0, np.int32))
+    fixtures.upload(gpu_ctx, sc2, one)
+    cam, env = fixtures.cam_env(sc["params"], 40)
+    env[4] = 0.7
+    want, _ = oracle.render(sc2, cam, env, 1600, 3, 4, one)
+    assert np.array_equal(bits(gpu_ctx.render(cam, env, 40, 40, 3, 4)), bits(want))
+
+
+def test_nan_and_inf_semantics_survive(gpu_ctx):
+    """inf * 0 -> NaN -> fmax(fmin(NaN,1),0) = 1 (white pixel) must come out as in the reference."""
+    sc = fixtures.load_scene("cornell")
+    ibl = fixtures.load_ibl()
+    mat = sc["materialData"].copy()
+    mat[4::6] = np.inf          # emissive power slot = +inf for every material
+    mat[0] = 0                  # material 0 becomes an emitter of infinite power
+    sc2 = dict(sc, materialData=mat)
+    fixtures.upload(gpu_ctx, sc2, ibl)
+    cam, env = fixtures.cam_env(sc["params"], 48)
+    want, _ = oracle.render(sc2, cam, env, 48 * 48, 4, 4, ibl)
+    out = gpu_ctx.render(cam, env, 48, 48, 4, 4)
+    assert np.array_equal(bits(out), bits(want))
+
+
+def test_tonemap_golden_and_oracle(gpu_ctx):
+    g = fixtures.golden()
+    x = g["tonemap/in"]
+    out = np.zeros_like(x)
+    gpu_ctx.img_processing(x, out, 600)
+    assert np.array_equal(bits(out), bits(g["tonemap/out"]))
+    x = np.random.default_rng(3).uniform(0, 1.3, 1 << 20).astype(np.float32)
+    out = np.full_like(x, -7.0)
+    gpu_ctx.img_processing(x, out, x.size - 100)
+    assert np.array_equal(bits(out[:-100]), bits(oracle.img_processing(x, x.size - 100)[:-100]))
+    assert np.all(out[-100:] == -7.0)   # work-items with i >= N write nothing
+
+
+def test_finalize_and_reduce_kernels(gpu_ctx):
+    import torch
+    r = np.random.default_rng(8)
+    n_pix, spp = 12345, 7
+    parts = [torch.tensor(r.uniform(-1, 5, n_pix * 3).astype(np.float32), device="cuda") for _ in range(3)]
+    out = torch.zeros(n_pix * 3, device="cuda")
+    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    gpu_ctx.finalize_device(parts[0].data_ptr(), out.data_ptr(), n_pix, spp)
+    torch.cuda.synchronize()
+    want = np.fmax(np.fmin(parts[0].cpu().numpy() / np.float32(spp), np.float32(1)), np.float32(0))
+    assert np.array_equal(bits(out.cpu().numpy()), bits(want))
+    gpu_ctx.reduce_finalize_device([p.data_ptr() for p in parts], out.data_ptr(), n_pix, spp)
+    torch.cuda.synchronize()
+    s = (parts[0].cpu().numpy() + parts[1].cpu().numpy()) + parts[2].cpu().numpy()
+    want = np.fmax(np.fmin(s / np.float32(spp), np.float32(1)), np.float32(0))
+    assert np.array_equal(bits(out.cpu().numpy()), bits(want))
+    gpu_ctx.set_stream(None)
