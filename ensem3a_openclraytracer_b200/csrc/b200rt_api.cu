@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <string>
@@ -49,6 +50,7 @@ struct b200rt_ctx {
   float root_box[6] = {0, 0, 0, 0, 0, 0};
   float cull_abs = 0.0f;
   int fast_div_ok = 1;
+  int quorum = 20;  // tuning knob, B200RT_QUORUM overrides
   std::vector<int32_t> tri_mat;  // for re-validating material edits
 
   // environment map
@@ -198,6 +200,7 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   A->tiles_x = (F.width + 7) / 8;
   int tiles_y = (F.height + 3) / 4;
   A->n_work = A->tiles_x * tiles_y * 32;
+  A->quorum = c->quorum;
 }
 
 int effective_traversal(const b200rt_ctx *c, const b200rt_opts &o) {
@@ -426,6 +429,10 @@ int b200rt_create(int device, b200rt_ctx **out) {
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   memset(&c->stats, 0, sizeof c->stats);
+  if (const char *q = getenv("B200RT_QUORUM")) {
+    int v = atoi(q);
+    if (v >= 1 && v <= 32) c->quorum = v;
+  }
   auto bail = [&](const char *what, cudaError_t err) {
     fail(nullptr, B200RT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
     delete c;

@@ -31,6 +31,7 @@ struct KernelArgs {
   int stack_depth;        // entries per lane
   int n_work;             // work items (32-pixel tiles x 32)
   int tiles_x;
+  int quorum;             // k_paths leaves its traversal loop when fewer lanes than this are still traversing
 };
 
 // ---- shared-memory staging of a small scene with the bulk-copy engine (TMA 1-D) ------------------------
@@ -175,6 +176,11 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
 }
 
 // ---- path tracer ----------------------------------------------------------------------------------------------
+// Lane phases.  A lane always holds at most one ray; `T.active` says its traversal is still running.
+//   PH_NONE    between samples (or no pixel): start the next sample from the cached primary hit
+//   PH_SHADE   the segment hit a non-emissive surface: sample the next direction (Raytracing.cl:51-87)
+//   PH_BOUNCE  a bounce ray is being traced / has just finished (:82-110)
+//   PH_SUN     the sun shadow ray is being traced / has just finished (:115-137)
 enum { PH_NONE = 0, PH_SHADE = 1, PH_BOUNCE = 2, PH_SUN = 3 };
 
 template <int TRAV, bool SMEM, bool STATS>
@@ -195,10 +201,13 @@ __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ Kernel
   float seg_k = 0.0f;
   int seg_tri = -1;
   int seg_type = 0;                                // material type of the surface the pending ray left
-  v3 ray_o = mk3(0, 0, 0), ray_d = mk3(0, 0, 0);  // pending ray
   v3 acc = mk3(0, 0, 0), sum = mk3(0, 0, 0);
   rng_state g;
   g.a = 0;
+  Trav T;                                          // the pending ray and its traversal
+  T.active = false;
+  T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0; T.cur = 0; T.sp = 0;
+  T.R.o = mk3(0, 0, 0); T.R.d = mk3(0, 0, 0); T.R.r = mk3(0, 0, 0); T.R.fast = false;
   bool exhausted = false;
 
   unsigned long long rays = 0, samples = 0;
@@ -207,95 +216,18 @@ __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ Kernel
   tc.box_tests = 0; tc.tri_tests = 0;
 
   for (;;) {
-    // -------- refill: lanes without a pixel fetch the next work item ------------------------------------------
-    for (;;) {
-      unsigned int need = __ballot_sync(0xffffffffu, pix < 0);
-      if (need == 0u || exhausted) break;
-      unsigned int base = 0;
-      const int leader = __ffs(need) - 1;
-      const unsigned int cnt = __popc(need);
-      if ((int)lane == leader) base = atomicAdd(A.work_counter, cnt);
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (base + cnt >= (unsigned)A.n_work) exhausted = true;
-      if (pix < 0) {
-        unsigned int w = base + __popc(need & lt_mask);
-        if (w < (unsigned)A.n_work) {
-          int i = work_to_pixel(A, w);
-          if (i >= 0) {
-            int t = A.prim_tri[i];
-            if (t >= 0) {
-              pix = i;
-              s = F.s0;
-              sum = mk3(0.0f, 0.0f, 0.0f);
-              g.a = (uint32_t)i;  // Raytracing.cl:171 (imgSize receives imgDim, so seed0 = i)
-              phase = PH_NONE;
-            }
-          }
-        }
-      }
-    }
-    if (__ballot_sync(0xffffffffu, pix >= 0) == 0u) break;
+    // ======== phase A: every lane that is not traversing is moved forward until it has a ray again ==========
+    bool new_ray = false;
 
-    // -------- start of a sample: reload the cached primary hit (Raytracing.cl:195-201) --------------------------
-    if (pix >= 0 && phase == PH_NONE) {
-      float4 dk = A.prim_dirk[pix];
-      seg_o = F.cam_pos;
-      seg_d = mk3(dk.x, dk.y, dk.z);
-      seg_k = dk.w;
-      seg_tri = A.prim_tri[pix];
-      acc = mk3(1.0f, 1.0f, 1.0f);
-      j = 0;
-      phase = PH_SHADE;
-    }
-
-    // -------- shade: choose the next direction and fold BRDF * cos / pdf into the sample (:51-87) ------------------
-    if (phase == PH_SHADE) {
-      float4 t2 = ld4<SMEM>(S.tris + 3 * (size_t)seg_tri + 2);
-      float4 nn = ld4<SMEM>(S.normals + seg_tri);
-      v3 n = mk3(nn.x, nn.y, nn.z);
-      Material m = load_material(S.mats, __float_as_int(t2.y));
-      v3 nd, brdf;
-      float inv_pdf;
-      if (m.type == 3) {
-        nd = seg_d;
-        brdf = m.color;
-        inv_pdf = 1.0f / fabsf(dot(nd, unit(n)));
-      } else {
-        float u0, u1;
-        if (F.rng_mode == 0) draw2<0>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
-        else draw2<1>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
-        if (m.type == 1) {
-          nd = sample_cosine(n, u0, u1, &inv_pdf);
-          brdf = m.color * (1.0f / 3.14f);
-        } else {
-          nd = sample_uniform(n, u0, u1, &inv_pdf);
-          brdf = bsdf_ggx(m, neg3(seg_d), nd, n);
-        }
-      }
-      ray_o = seg_o + unit(seg_d) * seg_k;  // :79 — no offset along the normal
-      ray_d = nd;
-      float att = inv_pdf * fabsf(dot(nd, unit(n)));
-      acc = (acc * brdf) * att;
-      seg_type = m.type;
-      phase = PH_BOUNCE;
-    }
-
-    // -------- trace the pending ray --------------------------------------------------------------------------------
-    Hit h;
-    h.tri = -1; h.k = 1000.0f;
-    if (pix >= 0) {
-      h = closest_hit<TRAV, SMEM, STATS>(S, ray_o, ray_d, st, &tc, &mism);
-      rays++;
-    }
-
-    // -------- resolve -------------------------------------------------------------------------------------------------
-    if (pix >= 0) {
+    // A1 resolve a finished trace
+    if (pix >= 0 && !T.active && (phase == PH_BOUNCE || phase == PH_SUN)) {
+      const Hit h = T.best;
       bool end_sample = false;
       if (phase == PH_BOUNCE) {
         if (h.tri >= 0) {
           int mat = __float_as_int(ld4<SMEM>(S.tris + 3 * (size_t)h.tri + 2).y);
           Material mb = load_material(S.mats, mat);
-          seg_o = ray_o; seg_d = ray_d; seg_k = h.k; seg_tri = h.tri;
+          seg_o = T.R.o; seg_d = T.R.d; seg_k = h.k; seg_tri = h.tri;
           if (mb.type != 0) {
             if (j == F.max_bounce) {  // :99-103
               acc = mk3(0.0f, 0.0f, 0.0f);
@@ -309,9 +241,10 @@ __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ Kernel
             end_sample = true;
           }
         } else {  // escaped: shadow ray towards the sun from the same origin (:115-124)
-          seg_d = ray_d;
-          ray_d = F.sun_dir;
+          seg_d = T.R.d;
+          T.R.d = F.sun_dir;
           phase = PH_SUN;
+          new_ray = true;
         }
       } else {  // PH_SUN, :125-137
         v3 sun = mk3(0.0f, 0.0f, 0.0f);
@@ -335,6 +268,100 @@ __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ Kernel
           write_pixel(A, pix, sum);
           pix = -1;
         }
+      }
+    }
+
+    // A2 refill: lanes without a pixel fetch the next work item (one warp-aggregated atomic)
+    {
+      unsigned int need = __ballot_sync(0xffffffffu, pix < 0);
+      if (need != 0u && !exhausted) {
+        unsigned int base = 0;
+        const int leader = __ffs(need) - 1;
+        const unsigned int cnt = __popc(need);
+        if ((int)lane == leader) base = atomicAdd(A.work_counter, cnt);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (base + cnt >= (unsigned)A.n_work) exhausted = true;
+        if (pix < 0) {
+          unsigned int w = base + __popc(need & lt_mask);
+          if (w < (unsigned)A.n_work) {
+            int i = work_to_pixel(A, w);
+            if (i >= 0 && A.prim_tri[i] >= 0) {
+              pix = i;
+              s = F.s0;
+              sum = mk3(0.0f, 0.0f, 0.0f);
+              g.a = (uint32_t)i;  // Raytracing.cl:171 (imgSize receives imgDim, so seed0 = i)
+              phase = PH_NONE;
+            }
+          }
+        }
+      }
+    }
+
+    // A3 start of a sample: reload the cached primary hit (Raytracing.cl:195-201)
+    if (pix >= 0 && phase == PH_NONE) {
+      float4 dk = A.prim_dirk[pix];
+      seg_o = F.cam_pos;
+      seg_d = mk3(dk.x, dk.y, dk.z);
+      seg_k = dk.w;
+      seg_tri = A.prim_tri[pix];
+      acc = mk3(1.0f, 1.0f, 1.0f);
+      j = 0;
+      phase = PH_SHADE;
+    }
+
+    // A4 shade: choose the next direction and fold BRDF * cos / pdf into the sample (:51-87)
+    if (pix >= 0 && phase == PH_SHADE) {
+      float4 t2 = ld4<SMEM>(S.tris + 3 * (size_t)seg_tri + 2);
+      float4 nn = ld4<SMEM>(S.normals + seg_tri);
+      v3 n = mk3(nn.x, nn.y, nn.z);
+      Material m = load_material(S.mats, __float_as_int(t2.y));
+      v3 nd, brdf;
+      float inv_pdf;
+      if (m.type == 3) {
+        nd = seg_d;
+        brdf = m.color;
+        inv_pdf = 1.0f / fabsf(dot(nd, unit(n)));
+      } else {
+        float u0, u1;
+        if (F.rng_mode == 0) draw2<0>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
+        else draw2<1>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
+        if (m.type == 1) {
+          nd = sample_cosine(n, u0, u1, &inv_pdf);
+          brdf = m.color * (1.0f / 3.14f);
+        } else {
+          nd = sample_uniform(n, u0, u1, &inv_pdf);
+          brdf = bsdf_ggx(m, neg3(seg_d), nd, n);
+        }
+      }
+      T.R.o = seg_o + unit(seg_d) * seg_k;  // :79 — no offset along the normal
+      T.R.d = nd;
+      float att = inv_pdf * fabsf(dot(nd, unit(n)));
+      acc = (acc * brdf) * att;
+      seg_type = m.type;
+      phase = PH_BOUNCE;
+      new_ray = true;
+    }
+
+    // A5 the new ray enters the tree
+    if (new_ray) {
+      rays++;
+      if (TRAV == 0) {
+        trav_begin<SMEM, STATS>(S, T, T.R.o, T.R.d, &tc);
+      } else {  // reference / verify traversal: the whole walk at once
+        T.best = closest_hit<TRAV, SMEM, STATS>(S, T.R.o, T.R.d, st, &tc, &mism);
+        T.active = false;
+      }
+    }
+
+    // ======== phase B: advance all running traversals, one node per turn, while enough lanes take part ==========
+    const unsigned int alive = exhausted ? __ballot_sync(0xffffffffu, pix >= 0) : 0xffffffffu;
+    if (alive == 0u) break;
+    if (TRAV == 0) {
+      const int quorum = min(A.quorum, __popc(alive));
+      for (;;) {
+        const unsigned int act = __ballot_sync(0xffffffffu, T.active);
+        if (__popc(act) < quorum) break;
+        if (T.active) trav_step<SMEM, STATS>(S, T, st, &tc);
       }
     }
   }

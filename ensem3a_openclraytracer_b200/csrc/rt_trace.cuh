@@ -264,6 +264,102 @@ RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, TraceC
   return traverse_fast<SMEM, STATS, false>(S, R, st, cnt);
 }
 
+// ---- the same fast traversal, one node per call -------------------------------------------------------------------
+// k_paths keeps every lane's traversal in registers and advances all of them one node at a time, so that
+// a warp can leave the traversal loop as soon as too few of its lanes are still traversing, shade the
+// finished ones into new rays and come back — instead of idling until its longest ray is done.
+struct Trav {
+  RayDiv R;
+  Hit best;
+  int best_rank;
+  int cur, sp;
+  bool active;
+};
+
+template <bool SMEM, bool STATS>
+RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, TraceCounters *cnt) {
+  T.R = make_raydiv(o, d, S.fast_div_ok != 0);
+  T.best.tri = -1;
+  T.best.k = 1000.0f;
+  T.best_rank = 0x7fffffff;
+  T.cur = 0;
+  T.sp = 0;
+  float tmin, tmax;
+  if (STATS) cnt->box_tests++;
+  bool hit = T.R.fast ? slab<true>(T.R, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
+                                   S.root_box[5], &tmin, &tmax)
+                      : slab<false>(T.R, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
+                                    S.root_box[5], &tmin, &tmax);
+  T.active = hit;
+  if (hit && S.root_ref < 0) {
+    if (STATS) cnt->tri_tests++;
+    test_triangle<SMEM>(S, ~S.root_ref, o, d, T.best, T.best_rank);
+    T.active = false;
+  }
+}
+
+template <bool SMEM, bool STATS>
+RT_DEV void trav_step(const SceneView &S, Trav &T, LaneStack st, TraceCounters *cnt) {
+  const float4 *p = S.nodes + 4 * (size_t)T.cur;
+  float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
+  int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
+  float tminL, tmaxL, tminR, tmaxR;
+  bool goL, goR;
+  if (STATS) cnt->box_tests += 2;
+  if (T.R.fast) {
+    goL = slab<true>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
+    goR = slab<true>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
+  } else {
+    goL = slab<false>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
+    goR = slab<false>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
+  }
+  const float behind = -S.cull_abs;
+  float lim = T.best.k * 1.001f + S.cull_abs;
+  goL = goL && !(tminL > lim) && !(tmaxL < behind);
+  goR = goR && !(tminR > lim) && !(tmaxR < behind);
+  // leaves are tested at once (one triangle each); the nearer one first so that the farther can still be culled
+  bool leafL = goL && refL < 0, leafR = goR && refR < 0;
+  if (leafL || leafR) {
+    bool rightFirst = leafR && (!leafL || tminR < tminL);
+    int t0 = rightFirst ? ~refR : ~refL;
+    if (STATS) cnt->tri_tests++;
+    test_triangle<SMEM>(S, t0, T.R.o, T.R.d, T.best, T.best_rank);
+    lim = T.best.k * 1.001f + S.cull_abs;
+    if (leafL && leafR) {
+      float tOther = rightFirst ? tminL : tminR;
+      if (!(tOther > lim)) {
+        if (STATS) cnt->tri_tests++;
+        test_triangle<SMEM>(S, rightFirst ? ~refL : ~refR, T.R.o, T.R.d, T.best, T.best_rank);
+        lim = T.best.k * 1.001f + S.cull_abs;
+      }
+    }
+    goL = goL && !leafL && !(tminL > lim);
+    goR = goR && !leafR && !(tminR > lim);
+  }
+  if (goL && goR) {
+    bool leftNear = tminL <= tminR;
+    st.base[T.sp * st.stride] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? tminR : tminL);
+    ++T.sp;
+    T.cur = leftNear ? refL : refR;
+  } else if (goL) {
+    T.cur = refL;
+  } else if (goR) {
+    T.cur = refR;
+  } else {
+    bool found = false;
+    while (T.sp > 0) {
+      --T.sp;
+      float2 e = st.base[T.sp * st.stride];
+      if (!(e.y > T.best.k * 1.001f + S.cull_abs)) {
+        T.cur = __float_as_int(e.x);
+        found = true;
+        break;
+      }
+    }
+    T.active = found;
+  }
+}
+
 // TRAV: 0 fast, 1 reference, 2 verify (both; keeps reference, counts disagreements)
 template <int TRAV, bool SMEM, bool STATS>
 RT_DEV Hit closest_hit(const SceneView &S, v3 o, v3 d, LaneStack st, TraceCounters *cnt, unsigned int *mismatch) {
