@@ -50,7 +50,8 @@ struct b200rt_ctx {
   float root_box[6] = {0, 0, 0, 0, 0, 0};
   float cull_abs = 0.0f;
   int fast_div_ok = 1;
-  int quorum = 20;  // tuning knob, B200RT_QUORUM overrides
+  // k_paths tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_SLOTS override)
+  int quorum = 16, refill_min = 8, slots_per_lane = 3, tri_quorum = 16;
   std::vector<int32_t> tri_mat;  // for re-validating material edits
 
   // environment map
@@ -201,6 +202,9 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   int tiles_y = (F.height + 3) / 4;
   A->n_work = A->tiles_x * tiles_y * 32;
   A->quorum = c->quorum;
+  A->refill_min = c->refill_min;
+  A->tri_quorum = c->tri_quorum;
+  A->slots_per_lane = c->slots_per_lane;
 }
 
 int effective_traversal(const b200rt_ctx *c, const b200rt_opts &o) {
@@ -263,7 +267,7 @@ int launch_primary(b200rt_ctx *c, const KernelArgs &A, int trav, bool smem, bool
 template <int TRAV, bool SMEM, bool STATS>
 int launch_paths_t(b200rt_ctx *c, const KernelArgs &A) {
   auto k = k_paths<TRAV, SMEM, STATS>;
-  size_t smem = smem_bytes(c, SMEM);
+  size_t smem = smem_bytes(c, SMEM) + path_extra_smem_bytes(A.slots_per_lane);
   if (set_smem_attr(c, k, smem)) return B200RT_ERR_CUDA;
   int grid = 0;
   if (persistent_grid(c, k, smem, &grid)) return B200RT_ERR_CUDA;
@@ -429,10 +433,16 @@ int b200rt_create(int device, b200rt_ctx **out) {
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   memset(&c->stats, 0, sizeof c->stats);
-  if (const char *q = getenv("B200RT_QUORUM")) {
-    int v = atoi(q);
-    if (v >= 1 && v <= 32) c->quorum = v;
-  }
+  auto env_int = [](const char *name, int lo, int hi, int *dst) {
+    if (const char *q = getenv(name)) {
+      int v = atoi(q);
+      if (v >= lo && v <= hi) *dst = v;
+    }
+  };
+  env_int("B200RT_QUORUM", 1, 32, &c->quorum);
+  env_int("B200RT_REFILL_MIN", 1, 32, &c->refill_min);
+  env_int("B200RT_SLOTS", 1, 8, &c->slots_per_lane);
+  env_int("B200RT_TRI_QUORUM", 1, 32, &c->tri_quorum);
   auto bail = [&](const char *what, cudaError_t err) {
     fail(nullptr, B200RT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
     delete c;

@@ -32,6 +32,9 @@ struct KernelArgs {
   int n_work;             // work items (32-pixel tiles x 32)
   int tiles_x;
   int quorum;             // k_paths leaves its traversal loop when fewer lanes than this are still traversing
+  int refill_min;         // idle lanes pull new rays once this many are idle
+  int tri_quorum;         // parked triangles are tested once this many lanes hold one
+  int slots_per_lane;     // path slots per lane in the warp's shared-memory pool
 };
 
 // ---- shared-memory staging of a small scene with the bulk-copy engine (TMA 1-D) ------------------------
@@ -176,12 +179,37 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
 }
 
 // ---- path tracer ----------------------------------------------------------------------------------------------
-// Lane phases.  A lane always holds at most one ray; `T.active` says its traversal is still running.
-//   PH_NONE    between samples (or no pixel): start the next sample from the cached primary hit
-//   PH_SHADE   the segment hit a non-emissive surface: sample the next direction (Raytracing.cl:51-87)
-//   PH_BOUNCE  a bounce ray is being traced / has just finished (:82-110)
-//   PH_SUN     the sun shadow ray is being traced / has just finished (:115-137)
-enum { PH_NONE = 0, PH_SHADE = 1, PH_BOUNCE = 2, PH_SUN = 3 };
+// One warp = one small wavefront renderer.  Each warp owns NS = 32 * slots_per_lane PATH SLOTS in shared
+// memory (structure of arrays, one pixel per slot, samples of a pixel strictly in order; the running sum of a
+// pixel lives in the output buffer).  The warp alternates between two phases:
+//
+//   phase A  (shade)     slots whose trace has finished, or that start a sample, are compacted into a list
+//                        with ballot/popc prefix sums and processed 32 at a time: resolve the hit, end/start
+//                        the sample, sample the next direction (Raytracing.cl:51-137).  Every processed slot
+//                        ends with a ray READY to trace (or becomes FREE when its pixel is complete).
+//   phase B  (traverse)  lanes pull READY rays from the compacted ray list and advance their traversals one
+//                        node per turn.  Leaves are parked and tested by the whole warp once `tri_quorum`
+//                        lanes hold one.  A lane whose ray is done hands the hit back to its slot and — as
+//                        soon as `refill_min` lanes are idle — the idle lanes pull the next rays together.
+//                        When the list is empty the warp keeps stepping until fewer than `quorum` lanes are
+//                        left, parks the unfinished traversals in shared memory and returns to phase A.
+//
+// FREE slots take new pixels from a global work counter (one warp-aggregated atomic per layer).
+enum SlotField { F_PIX = 0, F_META, F_RNG, F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_K, F_TRI, F_AX, F_AY, F_AZ, F_COUNT };
+// meta word: bits 0-2 state, bit 3 sun ray, bits 4-7 material type of the surface the ray left, bits 8-15 bounce j,
+// bits 16-31 sample index
+enum SlotState { ST_FREE = 0, ST_START = 1, ST_SHADE = 2, ST_READY = 3, ST_FLIGHT = 4, ST_DONE = 5 };
+RT_DEV uint32_t meta_pack(int state, int sun, int type, int j, int s) {
+  return (uint32_t)state | ((uint32_t)sun << 3) | ((uint32_t)(type & 15) << 4) | ((uint32_t)(j & 255) << 8) | ((uint32_t)s << 16);
+}
+constexpr int kTravSaveWords = 11;  // o, d, best.k, best.tri, best_rank, cur, sp
+
+__host__ __device__ inline size_t path_pool_bytes_per_warp(int slots_per_lane) {
+  return ((size_t)F_COUNT * 4u + 2u) * 32u * (size_t)slots_per_lane;  // fields + two uint8 lists
+}
+__host__ __device__ inline size_t path_extra_smem_bytes(int slots_per_lane) {  // beyond scene + stacks
+  return (size_t)kBlock * kTravSaveWords * 4u + (size_t)(kBlock / 32) * path_pool_bytes_per_warp(slots_per_lane);
+}
 
 template <int TRAV, bool SMEM, bool STATS>
 __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ KernelArgs A) {
@@ -194,21 +222,26 @@ __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ Kernel
   const FrameParams &F = A.F;
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int lt_mask = (1u << lane) - 1u;
+  const int K = A.slots_per_lane;
+  const int NS = 32 * K;
+  uint32_t *tsave = reinterpret_cast<uint32_t *>(smem + used + (size_t)kBlock * A.stack_depth * sizeof(float2)) + threadIdx.x;
+  uint32_t *pool = reinterpret_cast<uint32_t *>(smem + used + (size_t)kBlock * A.stack_depth * sizeof(float2) +
+                                                (size_t)kBlock * kTravSaveWords * 4u) +
+                   (threadIdx.x >> 5) * (path_pool_bytes_per_warp(K) / 4);
+  unsigned char *alist = reinterpret_cast<unsigned char *>(pool + F_COUNT * NS);
+  unsigned char *rlist = alist + NS;
+#define FLD(f, slot) pool[(f) * NS + (slot)]
+#define FLDF(f, slot) __uint_as_float(pool[(f) * NS + (slot)])
 
-  // lane state
-  int pix = -1, s = 0, j = 0, phase = PH_NONE;
-  v3 seg_o = mk3(0, 0, 0), seg_d = mk3(0, 0, 0);  // current segment (R_cam); after an escape: the escaped direction
-  float seg_k = 0.0f;
-  int seg_tri = -1;
-  int seg_type = 0;                                // material type of the surface the pending ray left
-  v3 acc = mk3(0, 0, 0), sum = mk3(0, 0, 0);
-  rng_state g;
-  g.a = 0;
-  Trav T;                                          // the pending ray and its traversal
-  T.active = false;
-  T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0; T.cur = 0; T.sp = 0;
-  T.R.o = mk3(0, 0, 0); T.R.d = mk3(0, 0, 0); T.R.r = mk3(0, 0, 0); T.R.fast = false;
+  for (int k = 0; k < K; ++k) {
+    FLD(F_PIX, k * 32 + lane) = 0xffffffffu;
+    FLD(F_META, k * 32 + lane) = meta_pack(ST_FREE, 0, 0, 0, 0);
+  }
+  __syncwarp();
+
+  int my_slot = -1;      // slot whose ray this lane is tracing (its traversal is parked in tsave during phase A)
   bool exhausted = false;
+  int pendingA = 0;      // slots waiting for phase A (uniform)
 
   unsigned long long rays = 0, samples = 0;
   unsigned int mism = 0;
@@ -216,155 +249,293 @@ __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ Kernel
   tc.box_tests = 0; tc.tri_tests = 0;
 
   for (;;) {
-    // ======== phase A: every lane that is not traversing is moved forward until it has a ray again ==========
-    bool new_ray = false;
-
-    // A1 resolve a finished trace
-    if (pix >= 0 && !T.active && (phase == PH_BOUNCE || phase == PH_SUN)) {
-      const Hit h = T.best;
-      bool end_sample = false;
-      if (phase == PH_BOUNCE) {
-        if (h.tri >= 0) {
-          int mat = __float_as_int(ld4<SMEM>(S.tris + 3 * (size_t)h.tri + 2).y);
-          Material mb = load_material(S.mats, mat);
-          seg_o = T.R.o; seg_d = T.R.d; seg_k = h.k; seg_tri = h.tri;
-          if (mb.type != 0) {
-            if (j == F.max_bounce) {  // :99-103
-              acc = mk3(0.0f, 0.0f, 0.0f);
-              end_sample = true;
-            } else {
-              ++j;
-              phase = PH_SHADE;
-            }
-          } else {  // :105-109
-            acc = acc * mb.roughness;
-            end_sample = true;
-          }
-        } else {  // escaped: shadow ray towards the sun from the same origin (:115-124)
-          seg_d = T.R.d;
-          T.R.d = F.sun_dir;
-          phase = PH_SUN;
-          new_ray = true;
-        }
-      } else {  // PH_SUN, :125-137
-        v3 sun = mk3(0.0f, 0.0f, 0.0f);
-        if (h.tri < 0) {
-          if (seg_type != 3) sun = mk3(F.sun_power, F.sun_power, F.sun_power);
-        } else {
-          int mat = __float_as_int(ld4<SMEM>(S.tris + 3 * (size_t)h.tri + 2).y);
-          Material ms = load_material(S.mats, mat);
-          if (ms.type == 3) sun = ms.color * F.sun_power;
-        }
-        v3 envl = ibl_lookup(F, A.ibl, seg_d) * F.ibl_power;
-        acc = acc * (sun + envl);
-        end_sample = true;
-      }
-      if (end_sample) {
-        sum = sum + acc;  // :207
-        ++s;
-        ++samples;
-        phase = PH_NONE;
-        if (s >= F.s1) {
-          write_pixel(A, pix, sum);
-          pix = -1;
-        }
-      }
-    }
-
-    // A2 refill: lanes without a pixel fetch the next work item (one warp-aggregated atomic)
-    {
-      unsigned int need = __ballot_sync(0xffffffffu, pix < 0);
-      if (need != 0u && !exhausted) {
+    // ===================================== phase A ==========================================================
+    // A0: FREE slots fetch pixels; a pixel that k_primary already finished leaves the slot FREE for the next round
+    for (;;) {
+      bool any_free = false;
+      for (int k = 0; k < K && !exhausted; ++k) {
+        const int slot = k * 32 + (int)lane;
+        const bool is_free = (FLD(F_META, slot) & 7u) == ST_FREE;
+        const unsigned int need = __ballot_sync(0xffffffffu, is_free);
+        if (need == 0u) continue;
         unsigned int base = 0;
         const int leader = __ffs(need) - 1;
         const unsigned int cnt = __popc(need);
         if ((int)lane == leader) base = atomicAdd(A.work_counter, cnt);
         base = __shfl_sync(0xffffffffu, base, leader);
         if (base + cnt >= (unsigned)A.n_work) exhausted = true;
-        if (pix < 0) {
+        bool still_free = is_free;
+        if (is_free) {
           unsigned int w = base + __popc(need & lt_mask);
           if (w < (unsigned)A.n_work) {
             int i = work_to_pixel(A, w);
             if (i >= 0 && A.prim_tri[i] >= 0) {
-              pix = i;
-              s = F.s0;
-              sum = mk3(0.0f, 0.0f, 0.0f);
-              g.a = (uint32_t)i;  // Raytracing.cl:171 (imgSize receives imgDim, so seed0 = i)
-              phase = PH_NONE;
+              FLD(F_PIX, slot) = (uint32_t)i;
+              FLD(F_RNG, slot) = (uint32_t)i;  // Raytracing.cl:171 (imgSize receives imgDim, so seed0 = i)
+              FLD(F_META, slot) = meta_pack(ST_START, 0, 0, 0, F.s0);
+              float *acc_px = A.out + 3 * (size_t)i;  // the pixel's running sum lives in the output buffer
+              acc_px[0] = 0.0f; acc_px[1] = 0.0f; acc_px[2] = 0.0f;
+              still_free = false;
             }
           }
         }
+        if (__ballot_sync(0xffffffffu, still_free) != 0u) any_free = true;
       }
+      if (!any_free || exhausted) break;
     }
+    __syncwarp();
 
-    // A3 start of a sample: reload the cached primary hit (Raytracing.cl:195-201)
-    if (pix >= 0 && phase == PH_NONE) {
-      float4 dk = A.prim_dirk[pix];
-      seg_o = F.cam_pos;
-      seg_d = mk3(dk.x, dk.y, dk.z);
-      seg_k = dk.w;
-      seg_tri = A.prim_tri[pix];
-      acc = mk3(1.0f, 1.0f, 1.0f);
-      j = 0;
-      phase = PH_SHADE;
+    // A1: compact the slots that need shading work into alist
+    int n_a = 0;
+    for (int k = 0; k < K; ++k) {
+      const int slot = k * 32 + (int)lane;
+      const unsigned int stt = FLD(F_META, slot) & 7u;
+      const bool want = (stt == ST_START) || (stt == ST_SHADE) || (stt == ST_DONE);
+      const unsigned int m = __ballot_sync(0xffffffffu, want);
+      if (want) alist[n_a + __popc(m & lt_mask)] = (unsigned char)slot;
+      n_a += __popc(m);
     }
+    __syncwarp();
 
-    // A4 shade: choose the next direction and fold BRDF * cos / pdf into the sample (:51-87)
-    if (pix >= 0 && phase == PH_SHADE) {
-      float4 t2 = ld4<SMEM>(S.tris + 3 * (size_t)seg_tri + 2);
-      float4 nn = ld4<SMEM>(S.normals + seg_tri);
-      v3 n = mk3(nn.x, nn.y, nn.z);
-      Material m = load_material(S.mats, __float_as_int(t2.y));
-      v3 nd, brdf;
-      float inv_pdf;
-      if (m.type == 3) {
-        nd = seg_d;
-        brdf = m.color;
-        inv_pdf = 1.0f / fabsf(dot(nd, unit(n)));
-      } else {
-        float u0, u1;
-        if (F.rng_mode == 0) draw2<0>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
-        else draw2<1>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
-        if (m.type == 1) {
-          nd = sample_cosine(n, u0, u1, &inv_pdf);
-          brdf = m.color * (1.0f / 3.14f);
+    // A2: process them 32 at a time; every processed slot ends READY (ray to trace) or FREE (pixel complete)
+    int n_ready = 0;
+    for (int c0 = 0; c0 < n_a; c0 += 32) {
+      const bool have = c0 + (int)lane < n_a;
+      bool ready = false;
+      int slot = 0;
+      if (have) {
+        slot = alist[c0 + lane];
+        const uint32_t meta = FLD(F_META, slot);
+        int state = (int)(meta & 7u), sun_ray = (int)((meta >> 3) & 1u), seg_type = (int)((meta >> 4) & 15u);
+        int j = (int)((meta >> 8) & 255u), s = (int)(meta >> 16);
+        const int pix = (int)FLD(F_PIX, slot);
+        v3 o = mk3(FLDF(F_OX, slot), FLDF(F_OY, slot), FLDF(F_OZ, slot));   // ray origin (DONE) / segment origin
+        v3 d = mk3(FLDF(F_DX, slot), FLDF(F_DY, slot), FLDF(F_DZ, slot));   // bounce direction; for a sun ray: the escaped direction
+        float hk = FLDF(F_K, slot);
+        int htri = (int)FLD(F_TRI, slot);
+        v3 acc = mk3(FLDF(F_AX, slot), FLDF(F_AY, slot), FLDF(F_AZ, slot));
+        bool pixel_done = false;
+
+        if (state == ST_DONE) {  // ---- resolve the finished trace
+          bool end_sample = false;
+          if (!sun_ray) {
+            if (htri >= 0) {  // the bounce ray becomes the current segment (:91-93)
+              int mat = __float_as_int(ld4<SMEM>(S.tris + 3 * (size_t)htri + 2).y);
+              Material mb = load_material(S.mats, mat);
+              if (mb.type != 0) {
+                if (j == F.max_bounce) {  // :99-103
+                  acc = mk3(0.0f, 0.0f, 0.0f);
+                  end_sample = true;
+                } else {
+                  ++j;
+                  state = ST_SHADE;
+                }
+              } else {  // :105-109
+                acc = acc * mb.roughness;
+                end_sample = true;
+              }
+            } else {  // escaped: shadow ray towards the sun from the same origin (:115-124); d keeps the escaped direction
+              sun_ray = 1;
+              state = ST_READY;
+            }
+          } else {  // sun ray finished, :125-137
+            v3 sun = mk3(0.0f, 0.0f, 0.0f);
+            if (htri < 0) {
+              if (seg_type != 3) sun = mk3(F.sun_power, F.sun_power, F.sun_power);
+            } else {
+              int mat = __float_as_int(ld4<SMEM>(S.tris + 3 * (size_t)htri + 2).y);
+              Material ms = load_material(S.mats, mat);
+              if (ms.type == 3) sun = ms.color * F.sun_power;
+            }
+            v3 envl = ibl_lookup(F, A.ibl, d) * F.ibl_power;
+            acc = acc * (sun + envl);
+            end_sample = true;
+          }
+          if (end_sample) {
+            float *acc_px = A.out + 3 * (size_t)pix;
+            v3 sum = mk3(acc_px[0], acc_px[1], acc_px[2]);
+            sum = sum + acc;  // :207
+            ++s;
+            ++samples;
+            if (s >= F.s1) {
+              write_pixel(A, pix, sum);
+              pixel_done = true;
+            } else {
+              acc_px[0] = sum.x; acc_px[1] = sum.y; acc_px[2] = sum.z;
+              state = ST_START;
+            }
+          }
+        }
+
+        if (!pixel_done && state == ST_START) {  // ---- reload the cached primary hit (Raytracing.cl:195-201)
+          float4 dk = A.prim_dirk[pix];
+          o = F.cam_pos;
+          d = mk3(dk.x, dk.y, dk.z);
+          hk = dk.w;
+          htri = A.prim_tri[pix];
+          acc = mk3(1.0f, 1.0f, 1.0f);
+          j = 0;
+          state = ST_SHADE;
+        }
+
+        if (!pixel_done && state == ST_SHADE) {  // ---- next direction, BRDF * cos / pdf (:51-87); segment = (o, d, hk, htri)
+          float4 t2 = ld4<SMEM>(S.tris + 3 * (size_t)htri + 2);
+          float4 nn = ld4<SMEM>(S.normals + htri);
+          v3 n = mk3(nn.x, nn.y, nn.z);
+          Material m = load_material(S.mats, __float_as_int(t2.y));
+          v3 nd, brdf;
+          float inv_pdf;
+          if (m.type == 3) {
+            nd = d;
+            brdf = m.color;
+            inv_pdf = 1.0f / fabsf(dot(nd, unit(n)));
+          } else {
+            float u0, u1;
+            rng_state g;
+            g.a = FLD(F_RNG, slot);
+            if (F.rng_mode == 0) draw2<0>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
+            else draw2<1>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
+            FLD(F_RNG, slot) = g.a;
+            if (m.type == 1) {
+              nd = sample_cosine(n, u0, u1, &inv_pdf);
+              brdf = m.color * (1.0f / 3.14f);
+            } else {
+              nd = sample_uniform(n, u0, u1, &inv_pdf);
+              brdf = bsdf_ggx(m, neg3(d), nd, n);
+            }
+          }
+          o = o + unit(d) * hk;  // :79 — no offset along the normal
+          d = nd;
+          float att = inv_pdf * fabsf(dot(nd, unit(n)));
+          acc = (acc * brdf) * att;
+          seg_type = m.type;
+          sun_ray = 0;
+          state = ST_READY;
+        }
+
+        if (pixel_done) {
+          FLD(F_PIX, slot) = 0xffffffffu;
+          FLD(F_META, slot) = meta_pack(ST_FREE, 0, 0, 0, 0);
         } else {
-          nd = sample_uniform(n, u0, u1, &inv_pdf);
-          brdf = bsdf_ggx(m, neg3(seg_d), nd, n);
+          FLD(F_OX, slot) = __float_as_uint(o.x); FLD(F_OY, slot) = __float_as_uint(o.y); FLD(F_OZ, slot) = __float_as_uint(o.z);
+          FLD(F_DX, slot) = __float_as_uint(d.x); FLD(F_DY, slot) = __float_as_uint(d.y); FLD(F_DZ, slot) = __float_as_uint(d.z);
+          FLD(F_AX, slot) = __float_as_uint(acc.x); FLD(F_AY, slot) = __float_as_uint(acc.y); FLD(F_AZ, slot) = __float_as_uint(acc.z);
+          FLD(F_META, slot) = meta_pack(state, sun_ray, seg_type, j, s);
+          ready = (state == ST_READY);
         }
       }
-      T.R.o = seg_o + unit(seg_d) * seg_k;  // :79 — no offset along the normal
-      T.R.d = nd;
-      float att = inv_pdf * fabsf(dot(nd, unit(n)));
-      acc = (acc * brdf) * att;
-      seg_type = m.type;
-      phase = PH_BOUNCE;
-      new_ray = true;
+      const unsigned int rm = __ballot_sync(0xffffffffu, ready);
+      if (ready) rlist[n_ready + __popc(rm & lt_mask)] = (unsigned char)slot;
+      n_ready += __popc(rm);
+    }
+    pendingA = 0;
+    __syncwarp();
+
+    // nothing to trace, nothing in flight: either everything is finished or only FREE slots remain
+    if (n_ready == 0 && __ballot_sync(0xffffffffu, my_slot >= 0) == 0u) {
+      if (exhausted) break;
+      continue;
     }
 
-    // A5 the new ray enters the tree
-    if (new_ray) {
-      rays++;
-      if (TRAV == 0) {
-        trav_begin<SMEM, STATS>(S, T, T.R.o, T.R.d, &tc);
-      } else {  // reference / verify traversal: the whole walk at once
-        T.best = closest_hit<TRAV, SMEM, STATS>(S, T.R.o, T.R.d, st, &tc, &mism);
-        T.active = false;
+    // ===================================== phase B ==========================================================
+    Trav T;
+    Parked P;
+    P.n = 0; P.t0 = 0; P.t1 = 0; P.t2 = 0; P.t3 = 0;
+    T.active = false;
+    T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0x7fffffff; T.cur = 0; T.sp = 0;
+    T.R.o = mk3(0, 0, 0); T.R.d = mk3(1, 1, 1); T.R.r = mk3(1, 1, 1); T.R.fast = false;
+    if (my_slot >= 0) {  // un-park the traversal this lane left unfinished
+      v3 o = mk3(__uint_as_float(tsave[0 * kBlock]), __uint_as_float(tsave[1 * kBlock]), __uint_as_float(tsave[2 * kBlock]));
+      v3 d = mk3(__uint_as_float(tsave[3 * kBlock]), __uint_as_float(tsave[4 * kBlock]), __uint_as_float(tsave[5 * kBlock]));
+      T.R = make_raydiv(o, d, S.fast_div_ok != 0);
+      T.best.k = __uint_as_float(tsave[6 * kBlock]);
+      T.best.tri = (int)tsave[7 * kBlock];
+      T.best_rank = (int)tsave[8 * kBlock];
+      T.cur = (int)tsave[9 * kBlock];
+      T.sp = (int)tsave[10 * kBlock];
+      T.active = true;
+    }
+    int r_head = 0;
+    unsigned int last_nodem = 0xffffffffu;  // forces the bookkeeping path on the first turn
+    bool leave = false;
+    while (!leave) {
+      const bool can_node = T.active && P.n <= 2;
+      const unsigned int nodem = __ballot_sync(0xffffffffu, can_node);
+      const unsigned int parkm = __ballot_sync(0xffffffffu, P.n > 0);
+      const int n_park = __popc(parkm);
+      if (nodem == last_nodem && nodem != 0u && n_park < A.tri_quorum) {  // nothing changed: just step
+        if (can_node) trav_step_park<SMEM, STATS>(S, T, P, st, &tc);
+        continue;
+      }
+      // ---- parked triangles: tested by all lanes that hold one ------------------------------------------------
+      const int n_node = __popc(nodem);
+      if (n_park >= A.tri_quorum || (n_park > 0 && n_node < A.quorum)) {
+        while (__ballot_sync(0xffffffffu, P.n > 0) != 0u) {
+          if (P.n > 0) {
+            if (STATS) tc.tri_tests++;
+            test_triangle<SMEM>(S, unpark(P), T.R.o, T.R.d, T.best, T.best_rank);
+          }
+        }
+        last_nodem = 0xffffffffu;
+        continue;
+      }
+      // ---- hand finished hits back to their slots (a finished lane holds no parked triangle here) -----------------
+      const bool finished = (my_slot >= 0) && !T.active && P.n == 0;
+      if (finished) {
+        FLD(F_K, my_slot) = __float_as_uint(T.best.k);
+        FLD(F_TRI, my_slot) = (uint32_t)T.best.tri;
+        FLD(F_META, my_slot) = (FLD(F_META, my_slot) & ~7u) | ST_DONE;
+        my_slot = -1;
+      }
+      pendingA += __popc(__ballot_sync(0xffffffffu, finished));
+      // ---- idle lanes pull the next rays together ------------------------------------------------------------------
+      const unsigned int idle = __ballot_sync(0xffffffffu, my_slot < 0);
+      const int n_idle = __popc(idle);
+      const int avail = n_ready - r_head;
+      if (avail > 0 && (n_idle >= A.refill_min || n_idle == 32 || n_node < A.quorum)) {
+        const int rank = __popc(idle & lt_mask);
+        if (my_slot < 0 && rank < avail) {
+          my_slot = rlist[r_head + rank];
+          const uint32_t meta = FLD(F_META, my_slot);
+          FLD(F_META, my_slot) = (meta & ~7u) | ST_FLIGHT;
+          v3 o = mk3(FLDF(F_OX, my_slot), FLDF(F_OY, my_slot), FLDF(F_OZ, my_slot));
+          v3 d = ((meta >> 3) & 1u) ? F.sun_dir : mk3(FLDF(F_DX, my_slot), FLDF(F_DY, my_slot), FLDF(F_DZ, my_slot));
+          rays++;
+          if (TRAV == 0) {
+            trav_begin<SMEM, STATS>(S, T, o, d, &tc);
+          } else {  // reference / verify traversal: the whole walk at once
+            T.best = closest_hit<TRAV, SMEM, STATS>(S, o, d, st, &tc, &mism);
+            T.active = false;
+          }
+        }
+        r_head += min(n_idle, avail);
+        last_nodem = 0xffffffffu;  // lanes whose ray ended at the root box are handed back on the next turn
+        continue;
+      }
+      // ---- leave or keep stepping ---------------------------------------------------------------------------------------
+      if (n_node == 0) {
+        // no lane can step and nothing is parked (else the flush above ran): all remaining lanes are idle
+        leave = true;
+      } else if (avail == 0 && n_node < A.quorum && pendingA > 0) {
+        leave = true;
+      } else {
+        last_nodem = nodem;
       }
     }
-
-    // ======== phase B: advance all running traversals, one node per turn, while enough lanes take part ==========
-    const unsigned int alive = exhausted ? __ballot_sync(0xffffffffu, pix >= 0) : 0xffffffffu;
-    if (alive == 0u) break;
-    if (TRAV == 0) {
-      const int quorum = min(A.quorum, __popc(alive));
-      for (;;) {
-        const unsigned int act = __ballot_sync(0xffffffffu, T.active);
-        if (__popc(act) < quorum) break;
-        if (T.active) trav_step<SMEM, STATS>(S, T, st, &tc);
-      }
+    // park the unfinished traversals for the duration of phase A
+    if (my_slot >= 0) {
+      tsave[0 * kBlock] = __float_as_uint(T.R.o.x); tsave[1 * kBlock] = __float_as_uint(T.R.o.y); tsave[2 * kBlock] = __float_as_uint(T.R.o.z);
+      tsave[3 * kBlock] = __float_as_uint(T.R.d.x); tsave[4 * kBlock] = __float_as_uint(T.R.d.y); tsave[5 * kBlock] = __float_as_uint(T.R.d.z);
+      tsave[6 * kBlock] = __float_as_uint(T.best.k);
+      tsave[7 * kBlock] = (uint32_t)T.best.tri;
+      tsave[8 * kBlock] = (uint32_t)T.best_rank;
+      tsave[9 * kBlock] = (uint32_t)T.cur;
+      tsave[10 * kBlock] = (uint32_t)T.sp;
     }
+    __syncwarp();
   }
+#undef FLD
+#undef FLDF
 
   for (int o = 16; o > 0; o >>= 1) {
     rays += __shfl_down_sync(0xffffffffu, rays, o);

@@ -360,6 +360,81 @@ RT_DEV void trav_step(const SceneView &S, Trav &T, LaneStack st, TraceCounters *
   }
 }
 
+// Leaves found by a node step are not tested on the spot (only a few lanes of a warp reach a leaf in the
+// same turn) but parked here, at most four per lane; the warp tests parked triangles together once enough
+// lanes hold one.  First in, first out, so the nearer leaf of a pair is tested first.
+struct Parked {
+  int n, t0, t1, t2, t3;
+};
+RT_DEV void park(Parked &P, int t) {
+  if (P.n == 0) P.t0 = t;
+  else if (P.n == 1) P.t1 = t;
+  else if (P.n == 2) P.t2 = t;
+  else P.t3 = t;
+  ++P.n;
+}
+RT_DEV int unpark(Parked &P) {
+  int t = P.t0;
+  P.t0 = P.t1; P.t1 = P.t2; P.t2 = P.t3;
+  --P.n;
+  return t;
+}
+
+// one node; leaf children that pass their box test are parked instead of tested (needs P.n <= 2 on entry)
+template <bool SMEM, bool STATS>
+RT_DEV void trav_step_park(const SceneView &S, Trav &T, Parked &P, LaneStack st, TraceCounters *cnt) {
+  const float4 *p = S.nodes + 4 * (size_t)T.cur;
+  float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
+  int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
+  float tminL, tmaxL, tminR, tmaxR;
+  bool goL, goR;
+  if (STATS) cnt->box_tests += 2;
+  if (T.R.fast) {
+    goL = slab<true>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
+    goR = slab<true>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
+  } else {
+    goL = slab<false>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
+    goR = slab<false>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
+  }
+  const float lim = T.best.k * 1.001f + S.cull_abs;
+  goL = goL && !(tminL > lim) && !(tmaxL < -S.cull_abs);
+  goR = goR && !(tminR > lim) && !(tmaxR < -S.cull_abs);
+  const bool leafL = goL && refL < 0, leafR = goR && refR < 0;
+  if (leafL && leafR) {
+    const bool rightFirst = tminR < tminL;
+    park(P, rightFirst ? ~refR : ~refL);
+    park(P, rightFirst ? ~refL : ~refR);
+  } else if (leafL) {
+    park(P, ~refL);
+  } else if (leafR) {
+    park(P, ~refR);
+  }
+  goL = goL && !leafL;
+  goR = goR && !leafR;
+  if (goL && goR) {
+    const bool leftNear = tminL <= tminR;
+    st.base[T.sp * st.stride] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? tminR : tminL);
+    ++T.sp;
+    T.cur = leftNear ? refL : refR;
+  } else if (goL) {
+    T.cur = refL;
+  } else if (goR) {
+    T.cur = refR;
+  } else {
+    bool found = false;
+    while (T.sp > 0) {
+      --T.sp;
+      float2 e = st.base[T.sp * st.stride];
+      if (!(e.y > lim)) {
+        T.cur = __float_as_int(e.x);
+        found = true;
+        break;
+      }
+    }
+    T.active = found;
+  }
+}
+
 // TRAV: 0 fast, 1 reference, 2 verify (both; keeps reference, counts disagreements)
 template <int TRAV, bool SMEM, bool STATS>
 RT_DEV Hit closest_hit(const SceneView &S, v3 o, v3 d, LaneStack st, TraceCounters *cnt, unsigned int *mismatch) {
