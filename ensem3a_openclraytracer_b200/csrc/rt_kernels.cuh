@@ -72,16 +72,19 @@ RT_DEV SceneView stage_scene(const KernelArgs &A, unsigned char *smem, size_t *u
     bulk_g2s(s_tris, A.S.tris, tb, &bar);
     bulk_g2s(s_nrm, A.S.normals, nn, &bar);
   }
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(&bar))
-        : "memory");
+  if (threadIdx.x == 0) {  // one thread waits for the bytes to land; the block barrier publishes them
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(&bar))
+          : "memory");
+    }
   }
+  __syncthreads();
   S.nodes = s_nodes;
   S.tris = s_tris;
   S.normals = s_nrm;
@@ -202,7 +205,7 @@ enum SlotState { ST_FREE = 0, ST_START = 1, ST_SHADE = 2, ST_READY = 3, ST_FLIGH
 RT_DEV uint32_t meta_pack(int state, int sun, int type, int j, int s) {
   return (uint32_t)state | ((uint32_t)sun << 3) | ((uint32_t)(type & 15) << 4) | ((uint32_t)(j & 255) << 8) | ((uint32_t)s << 16);
 }
-constexpr int kTravSaveWords = 11;  // o, d, best.k, best.tri, best_rank, cur, sp
+constexpr int kTravSaveWords = 11 + kParkCap;  // o, d, best.k, best.tri, best_rank, cur, sp  +  parked leaves
 
 __host__ __device__ inline size_t path_pool_bytes_per_warp(int slots_per_lane) {
   return ((size_t)F_COUNT * 4u + 2u) * 32u * (size_t)slots_per_lane;  // fields + two uint8 lists
@@ -439,8 +442,8 @@ __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ Kernel
 
     // ===================================== phase B ==========================================================
     Trav T;
-    Parked P;
-    P.n = 0; P.t0 = 0; P.t1 = 0; P.t2 = 0; P.t3 = 0;
+    int pn = 0;                                  // parked leaves of this lane
+    uint32_t *parks = tsave + 11 * kBlock;       // entry e at parks[e * kBlock]
     T.active = false;
     T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0x7fffffff; T.cur = 0; T.sp = 0;
     T.R.o = mk3(0, 0, 0); T.R.d = mk3(1, 1, 1); T.R.r = mk3(1, 1, 1); T.R.fast = false;
@@ -459,28 +462,27 @@ __global__ void __launch_bounds__(kBlock) k_paths(const __grid_constant__ Kernel
     unsigned int last_nodem = 0xffffffffu;  // forces the bookkeeping path on the first turn
     bool leave = false;
     while (!leave) {
-      const bool can_node = T.active && P.n <= 2;
+      const bool can_node = T.active && pn <= kParkCap - 2;
       const unsigned int nodem = __ballot_sync(0xffffffffu, can_node);
-      const unsigned int parkm = __ballot_sync(0xffffffffu, P.n > 0);
+      const unsigned int parkm = __ballot_sync(0xffffffffu, pn > 0);
       const int n_park = __popc(parkm);
       if (nodem == last_nodem && nodem != 0u && n_park < A.tri_quorum) {  // nothing changed: just step
-        if (can_node) trav_step_park<SMEM, STATS>(S, T, P, st, &tc);
+        if (can_node) trav_step_park<SMEM, STATS>(S, T, pn, parks, kBlock, st, &tc);
         continue;
       }
-      // ---- parked triangles: tested by all lanes that hold one ------------------------------------------------
+      // ---- parked triangles: one round, every lane that holds one tests its most recent ------------------------
       const int n_node = __popc(nodem);
       if (n_park >= A.tri_quorum || (n_park > 0 && n_node < A.quorum)) {
-        while (__ballot_sync(0xffffffffu, P.n > 0) != 0u) {
-          if (P.n > 0) {
-            if (STATS) tc.tri_tests++;
-            test_triangle<SMEM>(S, unpark(P), T.R.o, T.R.d, T.best, T.best_rank);
-          }
+        if (pn > 0) {
+          --pn;
+          if (STATS) tc.tri_tests++;
+          test_triangle<SMEM>(S, (int)parks[pn * kBlock], T.R.o, T.R.d, T.best, T.best_rank);
         }
         last_nodem = 0xffffffffu;
         continue;
       }
       // ---- hand finished hits back to their slots (a finished lane holds no parked triangle here) -----------------
-      const bool finished = (my_slot >= 0) && !T.active && P.n == 0;
+      const bool finished = (my_slot >= 0) && !T.active && pn == 0;
       if (finished) {
         FLD(F_K, my_slot) = __float_as_uint(T.best.k);
         FLD(F_TRI, my_slot) = (uint32_t)T.best.tri;

@@ -50,19 +50,26 @@ RT_DEV float clamp01(float x) {
 }
 
 // ---- correctly-rounded binary32 transcendentals (binary64 evaluation, one rounding) ----
-RT_DEV float cr_sin(float a) { return __double2float_rn(sin((double)a)); }
-RT_DEV float cr_cos(float a) { return __double2float_rn(cos((double)a)); }
-RT_DEV void cr_sincos(float a, float *s, float *c) {
+// The binary64 routines are large; they are kept out of line so that the shading code holds one copy of each
+// and stays resident in the instruction cache next to the traversal loop.
+#define RT_NOINLINE __device__ __noinline__
+RT_NOINLINE float cr_sin(float a) { return __double2float_rn(sin((double)a)); }
+RT_NOINLINE float cr_cos(float a) { return __double2float_rn(cos((double)a)); }
+RT_NOINLINE float2 cr_sincos2(float a) {  // (sin, cos)
   double ds, dc;
   sincos((double)a, &ds, &dc);
-  *s = __double2float_rn(ds);
-  *c = __double2float_rn(dc);
+  return make_float2(__double2float_rn(ds), __double2float_rn(dc));
 }
-RT_DEV float cr_tan(float a) { return __double2float_rn(tan((double)a)); }
-RT_DEV float cr_acos(float a) { return __double2float_rn(acos((double)a)); }
-RT_DEV float cr_asin(float a) { return __double2float_rn(asin((double)a)); }
-RT_DEV float cr_atan2(float y, float x) { return __double2float_rn(atan2((double)y, (double)x)); }
-RT_DEV float cr_pow(float a, float b) { return __double2float_rn(pow((double)a, (double)b)); }
+RT_DEV void cr_sincos(float a, float *s, float *c) {
+  float2 r = cr_sincos2(a);
+  *s = r.x;
+  *c = r.y;
+}
+RT_NOINLINE float cr_tan(float a) { return __double2float_rn(tan((double)a)); }
+RT_NOINLINE float cr_acos(float a) { return __double2float_rn(acos((double)a)); }
+RT_NOINLINE float cr_asin(float a) { return __double2float_rn(asin((double)a)); }
+RT_NOINLINE float cr_atan2(float y, float x) { return __double2float_rn(atan2((double)y, (double)x)); }
+RT_NOINLINE float cr_pow(float a, float b) { return __double2float_rn(pow((double)a, (double)b)); }
 
 // ---- quaternion rotation, MathLib.cl:51-65 ------------------------------------------------
 RT_HD quat qmul(quat q, quat p) {

@@ -361,65 +361,67 @@ RT_DEV void trav_step(const SceneView &S, Trav &T, LaneStack st, TraceCounters *
 }
 
 // Leaves found by a node step are not tested on the spot (only a few lanes of a warp reach a leaf in the
-// same turn) but parked here, at most four per lane; the warp tests parked triangles together once enough
-// lanes hold one.  First in, first out, so the nearer leaf of a pair is tested first.
-struct Parked {
-  int n, t0, t1, t2, t3;
-};
-RT_DEV void park(Parked &P, int t) {
-  if (P.n == 0) P.t0 = t;
-  else if (P.n == 1) P.t1 = t;
-  else if (P.n == 2) P.t2 = t;
-  else P.t3 = t;
-  ++P.n;
-}
-RT_DEV int unpark(Parked &P) {
-  int t = P.t0;
-  P.t0 = P.t1; P.t1 = P.t2; P.t2 = P.t3;
-  --P.n;
-  return t;
+// same turn) but parked in a four-entry per-lane array in shared memory (entry e of lane l at parks[e * stride]);
+// the warp tests parked triangles together once enough lanes hold one.  Last in, first out; of a pair of
+// leaves the farther is parked first so that the nearer is tested first.
+constexpr int kParkCap = 4;
+
+// both children through the true-division slab test; out of line: only rays with a zero, denormal or huge
+// direction component come here
+// (everything by value so that no caller state is forced into local memory).  Returns (tminL, tminR, goL, goR)
+// with the verdicts as 1.0f / 0.0f and the "wholly behind the origin" cull already applied through `behind`.
+__device__ __noinline__ float4 slab_pair_slow(v3 o, v3 d, float4 q0, float4 q1, float4 q2, float behind) {
+  RayDiv R;
+  R.o = o; R.d = d; R.r = mk3(0.0f, 0.0f, 0.0f); R.fast = false;
+  float tminL, tmaxL, tminR, tmaxR;
+  bool goL = slab<false>(R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
+  bool goR = slab<false>(R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
+  goL = goL && !(tmaxL < behind);
+  goR = goR && !(tmaxR < behind);
+  return make_float4(tminL, tminR, goL ? 1.0f : 0.0f, goR ? 1.0f : 0.0f);
 }
 
-// one node; leaf children that pass their box test are parked instead of tested (needs P.n <= 2 on entry)
+// one node; leaf children that pass their box test are parked instead of tested (needs pn <= kParkCap - 2 on entry)
 template <bool SMEM, bool STATS>
-RT_DEV void trav_step_park(const SceneView &S, Trav &T, Parked &P, LaneStack st, TraceCounters *cnt) {
+RT_DEV void trav_step_park(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int pstride, LaneStack st,
+                           TraceCounters *cnt) {
   const float4 *p = S.nodes + 4 * (size_t)T.cur;
   float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
-  int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
-  float tminL, tmaxL, tminR, tmaxR;
+  const int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
+  float tminL, tminR;
   bool goL, goR;
   if (STATS) cnt->box_tests += 2;
   if (T.R.fast) {
+    float tmaxL, tmaxR;
     goL = slab<true>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
     goR = slab<true>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
+    goL = goL && !(tmaxL < -S.cull_abs);
+    goR = goR && !(tmaxR < -S.cull_abs);
   } else {
-    goL = slab<false>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
-    goR = slab<false>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
+    float4 r = slab_pair_slow(T.R.o, T.R.d, q0, q1, q2, -S.cull_abs);
+    tminL = r.x; tminR = r.y;
+    goL = r.z != 0.0f; goR = r.w != 0.0f;
   }
   const float lim = T.best.k * 1.001f + S.cull_abs;
-  goL = goL && !(tminL > lim) && !(tmaxL < -S.cull_abs);
-  goR = goR && !(tminR > lim) && !(tmaxR < -S.cull_abs);
+  goL = goL && !(tminL > lim);
+  goR = goR && !(tminR > lim);
   const bool leafL = goL && refL < 0, leafR = goR && refR < 0;
-  if (leafL && leafR) {
-    const bool rightFirst = tminR < tminL;
-    park(P, rightFirst ? ~refR : ~refL);
-    park(P, rightFirst ? ~refL : ~refR);
-  } else if (leafL) {
-    park(P, ~refL);
-  } else if (leafR) {
-    park(P, ~refR);
-  }
+  const bool both = leafL && leafR;
+  // parked last = tested first: the nearer leaf goes last
+  const bool rightNearer = both ? (tminR < tminL) : leafR;
+  const int nearerTri = rightNearer ? ~refR : ~refL;
+  const int fartherTri = rightNearer ? ~refL : ~refR;
+  if (both) { parks[pn * pstride] = (uint32_t)fartherTri; ++pn; }
+  if (leafL || leafR) { parks[pn * pstride] = (uint32_t)nearerTri; ++pn; }
   goL = goL && !leafL;
   goR = goR && !leafR;
+  const bool leftNear = tminL <= tminR;
   if (goL && goR) {
-    const bool leftNear = tminL <= tminR;
     st.base[T.sp * st.stride] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? tminR : tminL);
     ++T.sp;
     T.cur = leftNear ? refL : refR;
-  } else if (goL) {
-    T.cur = refL;
-  } else if (goR) {
-    T.cur = refR;
+  } else if (goL || goR) {
+    T.cur = goL ? refL : refR;
   } else {
     bool found = false;
     while (T.sp > 0) {

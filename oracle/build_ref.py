@@ -5,7 +5,7 @@ The reference hot path is OpenCL C (Kernels/Raytracing.cl, MathLib.cl, stack.cl,
 ImgProcessing.cl).  There is no OpenCL runtime in this image, so the sources are
 compiled as host C++ by g++ where they lie:
 
-  1. each .cl is read from <reference>/Kernels/ and written to oracle/_ref/ with two
+  1. each .cl is read from <reference>/Kernels/ and written to a TEMPORARY directory with two
      mechanical regex rewrites (no statement is added, removed or reordered):
         (floatN)(...) / (int2)(...)   ->  floatN(...) / int2(...)   vector literal -> ctor
         .yzw / .xyz                    ->  .yzw() / .xyz()            swizzle -> accessor
@@ -14,13 +14,14 @@ compiled as host C++ by g++ where they lie:
   2. oracle/ref_shim/ref_driver.cpp (#include "cl_shim.h", #include "Raytracing.cl")
      is compiled twice:  libclref.so (timing build) and libclref_count.so (counters).
 
-oracle/_ref/ is git-ignored (reference text never enters the history) but travels to the
-GPU box with the gpurun snapshot, where /root/reference does not exist.
+oracle/_ref/ holds only the resulting shared objects.  It is git-ignored but travels to the GPU box
+with the gpurun snapshot, where /root/reference does not exist; no reference text is stored anywhere.
 """
 import os
 import re
 import subprocess
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
@@ -57,20 +58,26 @@ def build(reference_root: str = "/root/reference", verbose: bool = True) -> bool
             print(f"[build_ref] {kdir} absent; prebuilt oracle/_ref libs {'found' if ok else 'MISSING'}")
         return ok
     os.makedirs(OUT, exist_ok=True)
-    for f in FILES:
-        with open(os.path.join(kdir, f), "r") as fh:
-            src = fh.read()
-        with open(os.path.join(OUT, f), "w") as fh:
-            fh.write(transpile(src))
-    drv = os.path.join(SHIM, "ref_driver.cpp")
-    for lib, extra in ((libs[0], []), (libs[1], ["-DCLREF_COUNTERS"])):
-        cmd = ["g++"] + CXXFLAGS + extra + ["-I", SHIM, "-I", OUT, drv, "-o", lib]
-        if verbose:
-            print("[build_ref]", " ".join(cmd))
-        subprocess.check_call(cmd)
-    # sensitivity build: glibc binary32 transcendentals instead of correctly-rounded ones
-    lib = os.path.join(OUT, "libclref_libmf.so")
-    subprocess.check_call(["g++"] + CXXFLAGS + ["-DCLREF_LIBM_FLOAT", "-I", SHIM, "-I", OUT, drv, "-o", lib])
+    for stale in FILES:  # earlier versions of this script left the rewritten text here
+        if os.path.exists(os.path.join(OUT, stale)):
+            os.remove(os.path.join(OUT, stale))
+    # the rewritten kernel text lives only in a temporary directory for the duration of the compile:
+    # oracle/_ref/ receives nothing but the shared objects
+    with tempfile.TemporaryDirectory(prefix="clref_") as tmp:
+        for f in FILES:
+            with open(os.path.join(kdir, f), "r") as fh:
+                src = fh.read()
+            with open(os.path.join(tmp, f), "w") as fh:
+                fh.write(transpile(src))
+        drv = os.path.join(SHIM, "ref_driver.cpp")
+        # timing build, counting build, and a sensitivity build (glibc binary32 transcendentals instead of
+        # correctly-rounded ones)
+        for lib, extra in ((libs[0], []), (libs[1], ["-DCLREF_COUNTERS"]),
+                           (os.path.join(OUT, "libclref_libmf.so"), ["-DCLREF_LIBM_FLOAT"])):
+            cmd = ["g++"] + CXXFLAGS + extra + ["-I", SHIM, "-I", tmp, drv, "-o", lib]
+            if verbose:
+                print("[build_ref]", " ".join(cmd))
+            subprocess.check_call(cmd)
     return True
 
 
