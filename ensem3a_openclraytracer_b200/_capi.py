@@ -34,7 +34,8 @@ class Stats(ctypes.Structure):
                 ("mismatches", ctypes.c_uint64), ("samples", ctypes.c_uint64), ("primary_ms", ctypes.c_float),
                 ("trace_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("upload_ms", ctypes.c_float),
                 ("kernel_launches", ctypes.c_int32), ("nodes", ctypes.c_int32), ("triangles", ctypes.c_int32),
-                ("bvh_depth", ctypes.c_int32), ("scene_in_smem", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3)]
+                ("bvh_depth", ctypes.c_int32), ("scene_in_smem", ctypes.c_int32), ("revalidated", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 2)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

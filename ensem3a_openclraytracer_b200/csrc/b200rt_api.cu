@@ -42,16 +42,16 @@ struct b200rt_ctx {
   bool have_scene = false;
   bool have_scene_cached = false;  // scene_hash / ibl_hash are valid
   uint64_t scene_hash = 0, mat_hash = 0;
-  DevBuf d_nodes, d_tris, d_normals, d_mats, d_bvh9;
+  DevBuf d_nodes, d_tris, d_normals, d_tboxes, d_mats, d_bvh9;
   int n_nodes9 = 0, n_inner = 0, n_tris = 0, n_mats = 0;
   int depth = 0, ref_stack_need = 0;
   bool canonical = true;
   int root_ref = 0;
   float root_box[6] = {0, 0, 0, 0, 0, 0};
-  float cull_abs = 0.0f;
-  int fast_div_ok = 1;
-  // k_paths tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_SLOTS override)
-  int quorum = 16, refill_min = 8, slots_per_lane = 3, tri_quorum = 16;
+  float cull_abs = 0.0f, cmax = 0.0f;
+  int fast_ok = 1;
+  // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
+  int quorum = 16, refill_min = 8, tri_quorum = 16, steps_per_turn = 2;
   std::vector<int32_t> tri_mat;  // for re-validating material edits
 
   // environment map
@@ -63,8 +63,8 @@ struct b200rt_ctx {
 
   // per-frame
   DevBuf d_prim_dirk, d_prim_tri, d_out, d_misc, d_tmp_a, d_tmp_b;
+  DevBuf d_pA, d_pB, d_pC, d_pHit, d_list0, d_list1, d_cnt;  // wavefront path state (rt_kernels.cuh)
   DeviceCounters *d_counters = nullptr;
-  unsigned int *d_work = nullptr;
 
   b200rt_stats stats;
   bool stats_pending = false;  // async render enqueued; counters/events not read yet
@@ -162,17 +162,12 @@ void frame_setup(const b200rt_ctx *c, const float *cam, const float *env, int wi
   F->key1 = (uint32_t)(o.seed >> 32);
 }
 
-bool use_smem_scene(const b200rt_ctx *c) {
-  size_t bytes = (size_t)c->n_inner * 64 + (size_t)c->n_tris * 64;
-  return bytes <= 64 * 1024;
-}
+size_t scene_smem_bytes(const b200rt_ctx *c) { return (size_t)c->n_inner * 64 + (size_t)c->n_tris * 48; }
 
-size_t stack_bytes(const b200rt_ctx *c) { return (size_t)kBlock * (size_t)(c->depth + 2) * sizeof(float2); }
+bool use_smem_scene(const b200rt_ctx *c) { return scene_smem_bytes(c) <= 48 * 1024; }
 
 size_t smem_bytes(const b200rt_ctx *c, bool smem_scene) {
-  size_t b = stack_bytes(c);
-  if (smem_scene) b += (size_t)c->n_inner * 64 + (size_t)c->n_tris * 64;
-  return b;
+  return lane_smem_bytes(c->depth + 2) + (smem_scene ? scene_smem_bytes(c) : 0);
 }
 
 void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float *d_out, KernelArgs *A) {
@@ -181,19 +176,28 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   S.nodes = static_cast<const float4 *>(c->d_nodes.p);
   S.tris = static_cast<const float4 *>(c->d_tris.p);
   S.normals = static_cast<const float4 *>(c->d_normals.p);
+  S.tboxes = static_cast<const float4 *>(c->d_tboxes.p);
   S.mats = static_cast<const float *>(c->d_mats.p);
   S.bvh9 = static_cast<const float *>(c->d_bvh9.p);
   S.root_ref = c->root_ref;
   for (int i = 0; i < 6; ++i) S.root_box[i] = c->root_box[i];
   S.cull_abs = c->cull_abs;
+  S.cmax = c->cmax;
   int cap = o.stack_cap <= 0 ? 20 : (o.stack_cap > 64 ? 64 : o.stack_cap);
   S.stack_cap = cap;
-  S.fast_div_ok = c->fast_div_ok;
+  S.fast_ok = c->fast_ok;
   A->ibl = c->ibl_tex;
   A->prim_dirk = static_cast<float4 *>(c->d_prim_dirk.p);
   A->prim_tri = static_cast<int *>(c->d_prim_tri.p);
   A->out = d_out;
-  A->work_counter = c->d_work;
+  A->pA = static_cast<float4 *>(c->d_pA.p);
+  A->pB = static_cast<float4 *>(c->d_pB.p);
+  A->pC = static_cast<float4 *>(c->d_pC.p);
+  A->pHit = static_cast<int2 *>(c->d_pHit.p);
+  A->list[0] = static_cast<int *>(c->d_list0.p);
+  A->list[1] = static_cast<int *>(c->d_list1.p);
+  A->cnt = static_cast<unsigned int *>(c->d_cnt.p);
+  A->wc = nullptr;
   A->counters = c->d_counters;
   A->n_nodes = c->n_inner;
   A->n_tris = c->n_tris;
@@ -204,7 +208,8 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   A->quorum = c->quorum;
   A->refill_min = c->refill_min;
   A->tri_quorum = c->tri_quorum;
-  A->slots_per_lane = c->slots_per_lane;
+  A->steps_per_turn = c->steps_per_turn;
+  A->validate = 0;
 }
 
 int effective_traversal(const b200rt_ctx *c, const b200rt_opts &o) {
@@ -264,34 +269,41 @@ int launch_primary(b200rt_ctx *c, const KernelArgs &A, int trav, bool smem, bool
   return fail(c, B200RT_ERR_INVALID, "bad traversal mode %d", trav);
 }
 
+// Launch geometry of the wavefront kernels, resolved once per frame (the occupancy queries are host calls)
+struct WaveLaunch {
+  void (*trace)(const KernelArgs, int) = nullptr;
+  int trace_grid = 0;
+  size_t trace_smem = 0;
+  int shade_grid = 0;
+};
+
 template <int TRAV, bool SMEM, bool STATS>
-int launch_paths_t(b200rt_ctx *c, const KernelArgs &A) {
-  auto k = k_paths<TRAV, SMEM, STATS>;
-  size_t smem = smem_bytes(c, SMEM) + path_extra_smem_bytes(A.slots_per_lane);
-  if (set_smem_attr(c, k, smem)) return B200RT_ERR_CUDA;
-  int grid = 0;
-  if (persistent_grid(c, k, smem, &grid)) return B200RT_ERR_CUDA;
-  int need = (A.n_work + kBlock - 1) / kBlock;
-  if (grid > need) grid = need;
-  k<<<grid, kBlock, smem, c->stream>>>(A);
-  CU(cudaGetLastError());
-  c->stats.kernel_launches++;
+int prepare_trace_t(b200rt_ctx *c, WaveLaunch *w) {
+  auto k = k_trace<TRAV, SMEM, STATS>;
+  w->trace_smem = smem_bytes(c, SMEM);
+  if (set_smem_attr(c, k, w->trace_smem)) return B200RT_ERR_CUDA;
+  if (persistent_grid(c, k, w->trace_smem, &w->trace_grid)) return B200RT_ERR_CUDA;
+  w->trace = k;
   return 0;
 }
 
-int launch_paths(b200rt_ctx *c, const KernelArgs &A, int trav, bool smem, bool stats) {
+int prepare_wave(b200rt_ctx *c, int trav, bool smem, bool stats, WaveLaunch *w) {
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, kShadeBlock, 0));
+  if (per_sm < 1) return fail(c, B200RT_ERR_CUDA, "k_shade does not fit on an SM");
+  w->shade_grid = per_sm * c->sm_count;
   int key = trav * 4 + (smem ? 2 : 0) + (stats ? 1 : 0);
   switch (key) {
-    case 0: return launch_paths_t<0, false, false>(c, A);
-    case 1: return launch_paths_t<0, false, true>(c, A);
-    case 2: return launch_paths_t<0, true, false>(c, A);
-    case 3: return launch_paths_t<0, true, true>(c, A);
-    case 4: return launch_paths_t<1, false, false>(c, A);
-    case 5: return launch_paths_t<1, false, true>(c, A);
-    case 6: return launch_paths_t<1, true, false>(c, A);
-    case 7: return launch_paths_t<1, true, true>(c, A);
-    case 8: case 9: return launch_paths_t<2, false, false>(c, A);
-    case 10: case 11: return launch_paths_t<2, true, false>(c, A);
+    case 0: return prepare_trace_t<0, false, false>(c, w);
+    case 1: return prepare_trace_t<0, false, true>(c, w);
+    case 2: return prepare_trace_t<0, true, false>(c, w);
+    case 3: return prepare_trace_t<0, true, true>(c, w);
+    case 4: return prepare_trace_t<1, false, false>(c, w);
+    case 5: return prepare_trace_t<1, false, true>(c, w);
+    case 6: return prepare_trace_t<1, true, false>(c, w);
+    case 7: return prepare_trace_t<1, true, true>(c, w);
+    case 8: case 9: return prepare_trace_t<2, false, false>(c, w);
+    case 10: case 11: return prepare_trace_t<2, true, false>(c, w);
   }
   return fail(c, B200RT_ERR_INVALID, "bad traversal mode %d", trav);
 }
@@ -320,6 +332,7 @@ int read_counters(b200rt_ctx *c) {
   c->stats.tri_tests = h.tri_tests;
   c->stats.mismatches = h.mismatches;
   c->stats.samples = h.samples;
+  c->stats.revalidated = (int32_t)(h.revalidated > 0x7fffffffull ? 0x7fffffffull : h.revalidated);
   float ms = 0;
   if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->stats.primary_ms = ms;
   if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->stats.trace_ms = ms;
@@ -369,25 +382,47 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   if (!c->have_ibl) return fail(c, B200RT_ERR_NO_SCENE, "no environment map: call b200rt_set_ibl first");
   CU(cudaSetDevice(c->device));
   const size_t npix = (size_t)width * height;
-  if (ensure(c, c->d_prim_dirk, npix * sizeof(float4))) return B200RT_ERR_CUDA;
-  if (ensure(c, c->d_prim_tri, npix * sizeof(int))) return B200RT_ERR_CUDA;
   FrameParams F;
   frame_setup(c, cam, env, width, height, spp, max_bounce, o, &F);
+  // every live path traces exactly one ray per iteration and a sample needs at most max_bounce + 1 bounce rays
+  // plus one sun ray (Raytracing.cl:46-137)
+  const long long n_iter_ll = (long long)(F.s1 - F.s0) * ((long long)max_bounce + 2);
+  if (n_iter_ll > (1 << 22)) return fail(c, B200RT_ERR_UNSUPPORTED, "spp x (maxBounce + 2) = %lld wavefront iterations exceed 2^22", n_iter_ll);
+  const int n_iter = (int)n_iter_ll;
+  if (ensure(c, c->d_prim_dirk, npix * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_prim_tri, npix * sizeof(int))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_pA, npix * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_pB, npix * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_pC, npix * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_pHit, npix * sizeof(int2))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_list0, npix * sizeof(int))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_list1, npix * sizeof(int))) return B200RT_ERR_CUDA;
+  const size_t n_cnt = (size_t)n_iter + 2;             // cnt[0 .. n_iter + 1]
+  const size_t cnt_bytes = (n_cnt + (size_t)n_iter + 1) * sizeof(unsigned int);  // then wc[0 .. n_iter]
+  if (ensure(c, c->d_cnt, cnt_bytes)) return B200RT_ERR_CUDA;
   KernelArgs A;
   fill_args(c, F, o, d_out, &A);
+  A.wc = A.cnt + n_cnt;
   const int trav = effective_traversal(c, o);
+  A.validate = (trav == B200RT_TRAVERSAL_FAST) ? 1 : 0;
   const bool smem = use_smem_scene(c);
+  WaveLaunch wl;
+  rc = prepare_wave(c, trav, smem, o.collect_stats != 0, &wl);
+  if (rc) return rc;
   c->stats.kernel_launches = 0;
   c->stats.scene_in_smem = smem ? 1 : 0;
-  CU(cudaMemsetAsync(c->d_prim_tri.p, 0xff, npix * sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
-  CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->stream));
+  CU(cudaMemsetAsync(c->d_cnt.p, 0, cnt_bytes, c->stream));
   CU(cudaEventRecord(c->ev[0], c->stream));
   rc = launch_primary(c, A, trav, smem, false, o.collect_stats != 0, nullptr, nullptr);
   if (rc) return rc;
   CU(cudaEventRecord(c->ev[1], c->stream));
-  rc = launch_paths(c, A, trav, smem, o.collect_stats != 0);
-  if (rc) return rc;
+  for (int it = 0; it <= n_iter; ++it) {
+    k_shade<<<wl.shade_grid, kShadeBlock, 0, c->stream>>>(A, it);
+    if (it < n_iter) wl.trace<<<wl.trace_grid, kBlock, wl.trace_smem, c->stream>>>(A, it);
+  }
+  CU(cudaGetLastError());
+  c->stats.kernel_launches += 2 * n_iter + 1;
   CU(cudaEventRecord(c->ev[2], c->stream));
   c->stats_pending = true;
   return 0;
@@ -441,7 +476,7 @@ int b200rt_create(int device, b200rt_ctx **out) {
   };
   env_int("B200RT_QUORUM", 1, 32, &c->quorum);
   env_int("B200RT_REFILL_MIN", 1, 32, &c->refill_min);
-  env_int("B200RT_SLOTS", 1, 8, &c->slots_per_lane);
+  env_int("B200RT_STEPS", 1, 16, &c->steps_per_turn);
   env_int("B200RT_TRI_QUORUM", 1, 32, &c->tri_quorum);
   auto bail = [&](const char *what, cudaError_t err) {
     fail(nullptr, B200RT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
@@ -454,7 +489,6 @@ int b200rt_create(int device, b200rt_ctx **out) {
   for (int i = 0; i < 3; ++i)
     if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&c->d_counters, sizeof(DeviceCounters))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&c->d_work, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
   *out = c;
   return 0;
 }
@@ -463,14 +497,14 @@ void b200rt_destroy(b200rt_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_mats, &c->d_bvh9, &c->d_prim_dirk,
-                    &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b};
+  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_mats, &c->d_bvh9, &c->d_prim_dirk,
+                    &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b, &c->d_pA, &c->d_pB, &c->d_pC,
+                    &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->ibl_tex) cudaDestroyTextureObject(c->ibl_tex);
   if (c->ibl_array) cudaFreeArray(c->ibl_array);
   if (c->d_counters) cudaFree(c->d_counters);
-  if (c->d_work) cudaFree(c->d_work);
   for (int i = 0; i < 3; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -528,9 +562,9 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   const int nvp = (int)(n_vp / 3), nvn = (int)(n_vn / 3), nm = (int)(n_mat / 6);
 
   // ---- triangles: validate indices, precompute edges exactly as MathLib.cl:129-130 rounds them -------------
-  std::vector<float4> tris((size_t)n_tris * 3), normals((size_t)n_tris);
+  std::vector<float4> tris((size_t)n_tris * 3), normals((size_t)n_tris), tboxes((size_t)n_tris * 2, make_float4(0, 0, 0, 0));
   std::vector<int32_t> tri_mat((size_t)n_tris);
-  float cmax = 0.0f, cmin_nz = INFINITY;
+  float cmax = 0.0f;
   for (int t = 0; t < n_tris; ++t) {
     const int32_t *f = face + 10 * (size_t)t;
     for (int j = 7; j < 10; ++j)
@@ -583,14 +617,30 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
       for (int k = 2; k < 8; ++k) {
         float v = std::fabs(bvh[9 * (size_t)cur + k]);
         if (!(v <= cmax)) cmax = v;
-        if (v > 0.0f && v < cmin_nz) cmin_nz = v;
       }
       bool leaf = (t != -1 && l == -1 && r == -1), inner = (t == -1 && l != -1 && r != -1);
       if (!leaf && !inner) canonical = false;
+      const float *bx = bvh + 9 * (size_t)cur + 2;
+      // the fast traversal's "leaf passes => ancestors pass" argument needs min <= max and child boxes nested in
+      // their parent's (rt_trace.cuh); BVH.py guarantees both, anything else is walked in reference order
+      for (int k = 0; k < 3; ++k)
+        if (!(bx[k] <= bx[k + 3])) canonical = false;
+      for (int ch : {l, r})
+        if (ch >= 0 && ch < n_nodes) {
+          const float *cb = bvh + 9 * (size_t)ch + 2;
+          for (int k = 0; k < 3; ++k)
+            if (!(cb[k] >= bx[k] && cb[k + 3] <= bx[k + 3])) canonical = false;
+        }
       if (t != -1) {
         int32_t old;
         memcpy(&old, &tris[3 * (size_t)t + 2].z, 4);
-        if (old == 0x7fffffff) memcpy(&tris[3 * (size_t)t + 2].z, &rank, 4);
+        if (old == 0x7fffffff) {
+          memcpy(&tris[3 * (size_t)t + 2].z, &rank, 4);
+          tboxes[2 * (size_t)t] = make_float4(bx[0], bx[1], bx[2], 0.0f);
+          tboxes[2 * (size_t)t + 1] = make_float4(bx[3], bx[4], bx[5], 0.0f);
+        } else {
+          canonical = false;  // a triangle held by two leaves: rank and leaf box would be ambiguous
+        }
         ++rank;
       }
       if (level[cur] > depth) depth = level[cur];
@@ -602,6 +652,7 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
     c->ref_stack_need = (int)max_stack;
   }
   if (!(cmax < INFINITY)) return fail(c, B200RT_ERR_INVALID, "scene contains a non-finite coordinate");
+  if (c->depth + 2 > kExactStack) canonical = false;  // closest_hit_exact's thread-local stack
 
   // ---- repack interior nodes breadth-first into the 64-byte two-child layout --------------------------------------
   std::vector<float4> nodes;
@@ -647,16 +698,21 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
     float dx = bvh[5] - bvh[2], dy = bvh[6] - bvh[3], dz = bvh[7] - bvh[4];
     c->cull_abs = 1e-3f * std::sqrt(dx * dx + dy * dy + dz * dz);
   }
-  c->fast_div_ok = (cmax <= 1.099511627776e12f && cmin_nz >= 8.673617379884035e-19f /* 2^-60 */) ? 1 : 0;
+  c->cmax = cmax;
+  // range the conservative slab test's error margin is proven for (rt_trace.cuh); outside it every ray takes
+  // closest_hit_exact
+  c->fast_ok = (cmax <= 1.099511627776e12f /* 2^40 */ && cmax >= 9.5367431640625e-07f /* 2^-20 */) ? 1 : 0;
 
   // ---- upload -------------------------------------------------------------------------------------------------------------
   CU(cudaSetDevice(c->device));
   if (ensure(c, c->d_tris, tris.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_normals, normals.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tboxes, tboxes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_nodes, nodes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_bvh9, (size_t)n_bvh * 4)) return B200RT_ERR_CUDA;
   CU(cudaMemcpyAsync(c->d_tris.p, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_normals.p, normals.data(), normals.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_tboxes.p, tboxes.data(), tboxes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   if (!nodes.empty())
     CU(cudaMemcpyAsync(c->d_nodes.p, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_bvh9.p, bvh, (size_t)n_bvh * 4, cudaMemcpyHostToDevice, c->stream));

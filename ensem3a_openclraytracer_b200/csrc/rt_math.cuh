@@ -168,23 +168,4 @@ RT_DEV void draw2(rng_state &g, uint32_t pixel, uint32_t sample, uint32_t bounce
   }
 }
 
-// ---- exact division by a per-ray constant -----------------------------------------------------------
-// q = RN(x / d) from r = RN(1/d): one multiply and two FMA correction steps.  After the first step q
-// is a faithful rounding of x/d; with a correctly-rounded reciprocal the second step is then the
-// correctly-rounded quotient (Markstein).  Valid when d, r and the quotient are normal and finite —
-// the traversal checks the ray's direction once (ray_div_safe) and falls back to true division
-// otherwise.  The sign of a zero quotient may differ from IEEE; the slab test only compares.
-RT_DEV float div_by(float x, float d, float r) {
-  float q = x * r;
-  float e = __fmaf_rn(-q, d, x);
-  q = __fmaf_rn(e, r, q);
-  e = __fmaf_rn(-q, d, x);
-  return __fmaf_rn(e, r, q);
-}
-
-RT_DEV bool div_safe(float d) {
-  float a = fabsf(d);
-  return a >= 9.094947017729282e-13f /* 2^-40 */ && a <= 1.099511627776e12f /* 2^40 */;
-}
-
 }  // namespace b200rt

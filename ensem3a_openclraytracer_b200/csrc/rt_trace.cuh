@@ -1,21 +1,36 @@
 // BVH traversal and ray/triangle intersection for the b200rt kernels.
 //
-// Contract: closest_hit_*() returns, for any ray, exactly the (triangle, distance) the
+// Contract: every closest-hit routine here returns, for any ray, exactly the (triangle, distance) the
 // reference's rayTrace() keeps (MathLib.cl:234-288):
-//   * a triangle is a candidate iff the slab test of MathLib.cl:167-190 — six TRUE divisions, a
-//     line/box test with no clipping to t >= 0 — passes for its leaf box and for every ancestor box,
-//     and Möller–Trumbore (MathLib.cl:117-160) reports k > 1e-7 with the reference's u/v rejections;
+//   * a triangle is a CANDIDATE iff the slab test of MathLib.cl:167-190 — six TRUE divisions, a line/box
+//     test with no clipping to t >= 0 — passes for its leaf box and for every ancestor box, and
+//     Möller–Trumbore (MathLib.cl:117-160) reports k > 1e-7 with the reference's u/v rejections;
 //   * among candidates with 1e-4 < k < 1000 the smallest k wins; equal k is resolved in favour of the
 //     triangle the reference visits first (it pushes left then right, so it walks right-first).
 //
-// Two implementations:
-//   closest_hit_reference  the reference's own visiting order on the as-is 9-float nodes, including
-//                          its capped stack that silently drops pushes (stack.cl:21-26);
-//   closest_hit_fast       front-to-back over a repacked 64-byte two-child node, sub-trees skipped when
-//                          their entry distance exceeds the best hit (plus a safety margin) or when
-//                          they lie wholly behind the origin, ties resolved by each triangle's
-//                          precomputed rank in the reference's visiting order.  Every box decision it
-//                          does take is the same exact slab test.
+// Implementations:
+//   closest_hit_reference  the reference's own visiting order on the as-is 9-float nodes, including its
+//                          capped stack that silently drops pushes (stack.cl:21-26);
+//   closest_hit_exact      front-to-back over the repacked 64-byte two-child nodes with the exact slab test
+//                          at every box (the fallback of the fast path, and the path of rays whose direction
+//                          has a zero / denormal / huge component);
+//   closest_hit_fast       the production path.  It rests on one observation about the reference's slab test:
+//
+//       For a ray whose direction components are all non-zero finite numbers, if a box B' is nested in a
+//       box B (B.min <= B'.min <= B'.max <= B.max per axis) then slab(B') passing implies slab(B) passing.
+//       Proof: RN(p - o) and RN(x / d) are monotone in p resp. x, so per axis the floating-point interval
+//       [min(t1,t2), max(t1,t2)] of B contains that of B'; hence tmin(B) <= tmin(B') and tmax(B) >= tmax(B'),
+//       and tmax(B') >= tmin(B') gives tmax(B) >= tmin(B).  (No NaN can arise: x / d with d != 0.)
+//
+//     BVH.py builds every node box as the exact float32 min/max over the node's triangles (BVH.py:43-70), so
+//     boxes are nested along every root-to-leaf chain (b200rt_set_scene verifies this; a tree that violates it
+//     is walked by closest_hit_reference).  A triangle is therefore a candidate iff its LEAF box passes the
+//     exact slab test and Möller–Trumbore accepts it; ancestor boxes matter for culling only.  The fast path
+//     walks the tree with a CONSERVATIVE slab test (one FMA per plane, widened by a proven error margin), runs
+//     the exact Möller–Trumbore on the leaves it reaches, and keeps the best hit; the winner's leaf box is
+//     then put through the exact slab test once (validate_hit).  If it passes — always, except for rays that
+//     graze a box edge within rounding — the winner is the reference's hit: the set searched is a superset of
+//     the candidates and its minimum is a candidate.  If it fails the ray is re-traced by closest_hit_exact.
 #pragma once
 #include "rt_math.cuh"
 
@@ -31,18 +46,21 @@ namespace b200rt {
 //   t0 = A.x A.y A.z e1.x     t1 = e1.y e1.z e2.x e2.y     t2 = e2.z mat rank -   (mat, rank int bits)
 //   with e1 = B - A, e2 = C - A rounded exactly as MathLib.cl:129-130 rounds them.
 // normal (16 B): first-vertex normal of the triangle (MathLib.cl:151), w unused.
+// leaf box (32 B, 2 x float4): min.xyz -, max.xyz -   of the leaf that holds the triangle (validate_hit).
 struct SceneView {
   const float4 *nodes;
   const float4 *tris;
   const float4 *normals;
+  const float4 *tboxes;
   const float *mats;        // 6 floats per material
   // as-is reference buffers for closest_hit_reference
   const float *bvh9;
   int root_ref;             // ~tri when the whole tree is one leaf
   float root_box[6];        // min xyz, max xyz of node 0
   float cull_abs;           // absolute part of the culling margin (1e-3 x scene diagonal)
+  float cmax;               // largest |coordinate| of any box plane
   int stack_cap;            // reference traversal
-  int fast_div_ok;          // scene coordinates small enough for div_by()
+  int fast_ok;              // scene coordinates in the range the conservative test is proven for
 };
 
 struct TraceCounters {
@@ -60,41 +78,70 @@ RT_DEV float4 ld4(const float4 *p) {
   return __ldg(p);
 }
 
-// ---- slab test --------------------------------------------------------------------------------------
-struct RayDiv {
-  v3 o, d, r;   // origin, direction, RN(1/direction)
-  bool fast;    // div_by() is valid for this ray
-};
-
-RT_DEV RayDiv make_raydiv(v3 o, v3 d, bool scene_ok) {
-  RayDiv R;
-  R.o = o; R.d = d;
-  R.fast = scene_ok && div_safe(d.x) && div_safe(d.y) && div_safe(d.z) &&
-           fabsf(o.x) <= 1.099511627776e12f && fabsf(o.y) <= 1.099511627776e12f && fabsf(o.z) <= 1.099511627776e12f;
-  R.r = mk3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));
-  return R;
-}
-
-// MathLib.cl:169-188.  FAST selects how the six quotients are formed, never what they are.
-template <bool FAST>
-RT_DEV bool slab(const RayDiv &R, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float *tmin,
-                 float *tmax) {
-  float a, b, lo, hi;
-  if (FAST) { a = div_by(mnx - R.o.x, R.d.x, R.r.x); b = div_by(mxx - R.o.x, R.d.x, R.r.x); }
-  else { a = __fdiv_rn(mnx - R.o.x, R.d.x); b = __fdiv_rn(mxx - R.o.x, R.d.x); }
-  lo = fminf(a, b);
-  hi = fmaxf(a, b);
-  if (FAST) { a = div_by(mny - R.o.y, R.d.y, R.r.y); b = div_by(mxy - R.o.y, R.d.y, R.r.y); }
-  else { a = __fdiv_rn(mny - R.o.y, R.d.y); b = __fdiv_rn(mxy - R.o.y, R.d.y); }
+// ---- exact slab test, MathLib.cl:169-188 --------------------------------------------------------------
+RT_DEV bool slab_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float *tmin,
+                       float *tmax) {
+  float a = __fdiv_rn(mnx - o.x, d.x), b = __fdiv_rn(mxx - o.x, d.x);
+  float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = __fdiv_rn(mny - o.y, d.y); b = __fdiv_rn(mxy - o.y, d.y);
   lo = fmaxf(lo, fminf(a, b));
   hi = fminf(hi, fmaxf(a, b));
-  if (FAST) { a = div_by(mnz - R.o.z, R.d.z, R.r.z); b = div_by(mxz - R.o.z, R.d.z, R.r.z); }
-  else { a = __fdiv_rn(mnz - R.o.z, R.d.z); b = __fdiv_rn(mxz - R.o.z, R.d.z); }
+  a = __fdiv_rn(mnz - o.z, d.z); b = __fdiv_rn(mxz - o.z, d.z);
   lo = fmaxf(lo, fminf(a, b));
   hi = fminf(hi, fmaxf(a, b));
   *tmin = lo;
   *tmax = hi;
   return hi >= lo;
+}
+
+// ---- conservative slab test ----------------------------------------------------------------------------
+// Per ray: r = RN(1/d) and, per axis, two constants so that for a plane coordinate p
+//     fma(p, r, c_near) <= t_exact(p) <= fma(p, r, c_far),      t_exact(p) = RN(RN(p - o) / d).
+// Error budget, with P = max(|p|, |o|) and u = 2^-24:  t_exact differs from the real (p - o)/d by at most
+// 4u·P|1/d|  (two roundings of a value of magnitude <= 2P/|d|);  fma(p, r, RN(-o·r)) differs from it by at most
+// u·2P|1/d| (r) + u·P|r| (o·r) + u·2P|r| (fma result) + u·P|r| (adding the margin)  < 7u·P|r|.
+// The margin  m = 2^-20 (cmax + |o|) |r| = 16u (cmax + |o|) |r|  covers the sum (11u·P|r|) with room to spare.
+// Valid while every |d| component lies in [2^-40, 2^40] and |o|, cmax <= 2^40 (no overflow, no denormal r).
+struct RayFast {
+  v3 r, ca, cb;  // ca goes with box.min, cb with box.max
+};
+
+RT_DEV bool comp_ok(float d) {
+  float a = fabsf(d);
+  return a >= 9.094947017729282e-13f /* 2^-40 */ && a <= 1.099511627776e12f /* 2^40 */;
+}
+
+RT_DEV bool ray_is_fast(const SceneView &S, v3 o, v3 d) {
+  return S.fast_ok != 0 && comp_ok(d.x) && comp_ok(d.y) && comp_ok(d.z) && fabsf(o.x) <= 1.099511627776e12f &&
+         fabsf(o.y) <= 1.099511627776e12f && fabsf(o.z) <= 1.099511627776e12f;
+}
+
+RT_DEV void rayfast_axis(float o, float d, float cmax, float *r, float *ca, float *cb) {
+  const float rr = __frcp_rn(d);
+  const float t0 = -(o * rr);
+  const float m = (9.5367431640625e-07f /* 2^-20 */ * (cmax + fabsf(o))) * fabsf(rr);
+  const float near = t0 - m, far = t0 + m;
+  *r = rr;
+  *ca = rr > 0.0f ? near : far;   // box.min is the near plane when the ray travels in +axis
+  *cb = rr > 0.0f ? far : near;
+}
+
+RT_DEV RayFast make_rayfast(const SceneView &S, v3 o, v3 d) {
+  RayFast Q;
+  rayfast_axis(o.x, d.x, S.cmax, &Q.r.x, &Q.ca.x, &Q.cb.x);
+  rayfast_axis(o.y, d.y, S.cmax, &Q.r.y, &Q.ca.y, &Q.cb.y);
+  rayfast_axis(o.z, d.z, S.cmax, &Q.r.z, &Q.ca.z, &Q.cb.z);
+  return Q;
+}
+
+// lo <= tmin_exact and hi >= tmax_exact of the same box; the box certainly fails when hi < lo
+RT_DEV void slab_cons(const RayFast &Q, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float *lo,
+                      float *hi) {
+  const float ax = __fmaf_rn(mnx, Q.r.x, Q.ca.x), bx = __fmaf_rn(mxx, Q.r.x, Q.cb.x);
+  const float ay = __fmaf_rn(mny, Q.r.y, Q.ca.y), by = __fmaf_rn(mxy, Q.r.y, Q.cb.y);
+  const float az = __fmaf_rn(mnz, Q.r.z, Q.ca.z), bz = __fmaf_rn(mxz, Q.r.z, Q.cb.z);
+  *lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+  *hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
 }
 
 // ---- Möller–Trumbore, MathLib.cl:117-160 ---------------------------------------------------------------
@@ -104,7 +151,7 @@ RT_DEV bool tri_hit(v3 o, v3 d, v3 A, v3 e1, v3 e2, float *k_out) {
   v3 h = cross(d, e2);
   float a = dot(e1, h);
   if (a > -eps && a < eps) return false;
-  float f = __fdiv_rn(1.0f, a);  // (float)(1.0 / (double)a) == RN(1/a): double rounding is innocuous for division
+  float f = __frcp_rn(a);  // (float)(1.0 / (double)a) == RN(1/a): the double rounding is innocuous for a reciprocal
   v3 s = o - A;
   float u = f * dot(s, h);
   if (u < 0.0f || u > 1.0f) return false;
@@ -131,13 +178,19 @@ RT_DEV void test_triangle(const SceneView &S, int t, v3 o, v3 d, Hit &best, int 
   }
 }
 
+// the exact slab test of the leaf box that holds triangle `tri` (global memory: once per ray)
+RT_DEV bool validate_hit(const SceneView &S, v3 o, v3 d, int tri) {
+  const float4 mn = __ldg(S.tboxes + 2 * (size_t)tri), mx = __ldg(S.tboxes + 2 * (size_t)tri + 1);
+  float lo, hi;
+  return slab_exact(o, d, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, &lo, &hi);
+}
+
 // ---- reference-order traversal ---------------------------------------------------------------------------
 template <bool SMEM, bool STATS>
 RT_DEV Hit closest_hit_reference(const SceneView &S, v3 o, v3 d, TraceCounters *cnt) {
   Hit best;
   best.tri = -1;
   best.k = 1000.0f;
-  RayDiv R = make_raydiv(o, d, false);
   int stack[64];
   int top = -1;
   const int cap = S.stack_cap;
@@ -147,7 +200,7 @@ RT_DEV Hit closest_hit_reference(const SceneView &S, v3 o, v3 d, TraceCounters *
     const float *n = S.bvh9 + 9 * (size_t)cur;
     float tmin, tmax;
     if (STATS) cnt->box_tests++;
-    if (!slab<false>(R, __ldg(n + 2), __ldg(n + 3), __ldg(n + 4), __ldg(n + 5), __ldg(n + 6), __ldg(n + 7), &tmin, &tmax))
+    if (!slab_exact(o, d, __ldg(n + 2), __ldg(n + 3), __ldg(n + 4), __ldg(n + 5), __ldg(n + 6), __ldg(n + 7), &tmin, &tmax))
       continue;
     int t = (int)__ldg(n + 8);
     if (t != -1) {
@@ -168,83 +221,48 @@ RT_DEV Hit closest_hit_reference(const SceneView &S, v3 o, v3 d, TraceCounters *
   return best;
 }
 
-// ---- fast traversal -------------------------------------------------------------------------------------------
-// Per-lane stack in shared memory: entry e of lane l lives at stack[e * stride + l] (bank-conflict free),
-// each entry = (node ref, entry distance).
-struct LaneStack {
-  float2 *base;   // already offset to this thread
-  int stride;     // threads per block
-};
+// ---- exact front-to-back traversal (fallback; thread-local stack) ----------------------------------------------
+constexpr int kExactStack = 64;   // b200rt_set_scene routes deeper trees to the reference traversal
 
-template <bool SMEM, bool STATS, bool FAST>
-RT_DEV Hit traverse_fast(const SceneView &S, const RayDiv &R, LaneStack st, TraceCounters *cnt) {
+template <bool SMEM>
+__device__ __noinline__ Hit closest_hit_exact(const SceneView &S, v3 o, v3 d) {
   Hit best;
   best.tri = -1;
   best.k = 1000.0f;
   int best_rank = 0x7fffffff;
-  const v3 o = R.o, d = R.d;
   float tmin, tmax;
-  if (STATS) cnt->box_tests++;
-  if (!slab<FAST>(R, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4], S.root_box[5], &tmin,
+  if (!slab_exact(o, d, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4], S.root_box[5], &tmin,
                   &tmax))
     return best;
   if (S.root_ref < 0) {
-    if (STATS) cnt->tri_tests++;
     test_triangle<SMEM>(S, ~S.root_ref, o, d, best, best_rank);
     return best;
   }
+  float2 stack[kExactStack];
   const float behind = -S.cull_abs;
-  int cur = 0;
-  int sp = 0;
+  int cur = 0, sp = 0;
   for (;;) {
     const float4 *p = S.nodes + 4 * (size_t)cur;
     float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
     int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
     float tminL, tmaxL, tminR, tmaxR;
-    if (STATS) cnt->box_tests += 2;
-    bool goL = slab<FAST>(R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
-    bool goR = slab<FAST>(R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
+    bool goL = slab_exact(o, d, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
+    bool goR = slab_exact(o, d, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
     float lim = best.k * 1.001f + S.cull_abs;
     goL = goL && !(tminL > lim) && !(tmaxL < behind);
     goR = goR && !(tminR > lim) && !(tmaxR < behind);
-    // leaves first (nearer one first so the other can be culled by the new limit)
-    if (goL && goR && refL < 0 && refR < 0 && tminR < tminL) {
-      if (STATS) cnt->tri_tests++;
-      test_triangle<SMEM>(S, ~refR, o, d, best, best_rank);
-      goR = false;
-      lim = best.k * 1.001f + S.cull_abs;
-      goL = !(tminL > lim);
-    }
-    if (goL && refL < 0) {
-      if (STATS) cnt->tri_tests++;
-      test_triangle<SMEM>(S, ~refL, o, d, best, best_rank);
-      goL = false;
-      lim = best.k * 1.001f + S.cull_abs;
-      goR = goR && !(tminR > lim);
-    }
-    if (goR && refR < 0) {
-      if (STATS) cnt->tri_tests++;
-      test_triangle<SMEM>(S, ~refR, o, d, best, best_rank);
-      goR = false;
-      lim = best.k * 1.001f + S.cull_abs;
-      goL = goL && !(tminL > lim);
-    }
+    if (goL && refL < 0) { test_triangle<SMEM>(S, ~refL, o, d, best, best_rank); goL = false; }
+    if (goR && refR < 0) { test_triangle<SMEM>(S, ~refR, o, d, best, best_rank); goR = false; }
     if (goL && goR) {
       bool leftNear = tminL <= tminR;
-      int farRef = leftNear ? refR : refL;
-      float farT = leftNear ? tminR : tminL;
-      st.base[sp * st.stride] = make_float2(__int_as_float(farRef), farT);
-      ++sp;
+      stack[sp++] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? tminR : tminL);
       cur = leftNear ? refL : refR;
-    } else if (goL) {
-      cur = refL;
-    } else if (goR) {
-      cur = refR;
+    } else if (goL || goR) {
+      cur = goL ? refL : refR;
     } else {
       bool found = false;
       while (sp > 0) {
-        --sp;
-        float2 e = st.base[sp * st.stride];
+        float2 e = stack[--sp];
         if (!(e.y > best.k * 1.001f + S.cull_abs)) {
           cur = __float_as_int(e.x);
           found = true;
@@ -257,167 +275,79 @@ RT_DEV Hit traverse_fast(const SceneView &S, const RayDiv &R, LaneStack st, Trac
   return best;
 }
 
-template <bool SMEM, bool STATS>
-RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, TraceCounters *cnt) {
-  RayDiv R = make_raydiv(o, d, S.fast_div_ok != 0);
-  if (R.fast) return traverse_fast<SMEM, STATS, true>(S, R, st, cnt);
-  return traverse_fast<SMEM, STATS, false>(S, R, st, cnt);
-}
+// ---- fast traversal ---------------------------------------------------------------------------------------------
+// Per-lane stack in shared memory: entry e of lane l lives at stack[e * stride + l] (bank-conflict free),
+// each entry = (node ref, conservative entry distance).
+struct LaneStack {
+  float2 *base;   // already offset to this thread
+  int stride;     // threads per block
+};
 
-// ---- the same fast traversal, one node per call -------------------------------------------------------------------
-// k_paths keeps every lane's traversal in registers and advances all of them one node at a time, so that
-// a warp can leave the traversal loop as soon as too few of its lanes are still traversing, shade the
-// finished ones into new rays and come back — instead of idling until its longest ray is done.
+// One traversal in flight.  Kept in registers; advanced one node at a time so that a warp can interleave
+// node steps, leaf tests and ray refills of its 32 lanes (k_trace), or simply looped (closest_hit_fast).
 struct Trav {
-  RayDiv R;
+  v3 o, d;
+  RayFast Q;
   Hit best;
   int best_rank;
   int cur, sp;
   bool active;
 };
 
+// Leaves whose box passes the conservative test are not tested on the spot (only a few lanes of a warp reach a
+// leaf in the same turn) but parked, at most kParkCap per lane (entry e of lane l at parks[e * stride]); the
+// warp tests parked triangles together.  Last in, first out; of a pair of leaves the farther is parked first.
+constexpr int kParkCap = 4;
+
+// starts a traversal of a ray for which ray_is_fast() holds
 template <bool SMEM, bool STATS>
-RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, TraceCounters *cnt) {
-  T.R = make_raydiv(o, d, S.fast_div_ok != 0);
+RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, int &pn, uint32_t *parks, TraceCounters *cnt) {
+  T.o = o; T.d = d;
+  T.Q = make_rayfast(S, o, d);
   T.best.tri = -1;
   T.best.k = 1000.0f;
   T.best_rank = 0x7fffffff;
   T.cur = 0;
   T.sp = 0;
-  float tmin, tmax;
+  float lo, hi;
   if (STATS) cnt->box_tests++;
-  bool hit = T.R.fast ? slab<true>(T.R, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
-                                   S.root_box[5], &tmin, &tmax)
-                      : slab<false>(T.R, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
-                                    S.root_box[5], &tmin, &tmax);
-  T.active = hit;
-  if (hit && S.root_ref < 0) {
-    if (STATS) cnt->tri_tests++;
-    test_triangle<SMEM>(S, ~S.root_ref, o, d, T.best, T.best_rank);
+  slab_cons(T.Q, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4], S.root_box[5], &lo, &hi);
+  T.active = hi >= lo;
+  if (T.active && S.root_ref < 0) {
+    parks[0] = (uint32_t)~S.root_ref;
+    pn = 1;
     T.active = false;
   }
 }
 
+// one node: both child boxes through the conservative test; leaf children are parked (needs pn <= kParkCap - 2)
 template <bool SMEM, bool STATS>
-RT_DEV void trav_step(const SceneView &S, Trav &T, LaneStack st, TraceCounters *cnt) {
+RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int pstride, LaneStack st,
+                      TraceCounters *cnt) {
   const float4 *p = S.nodes + 4 * (size_t)T.cur;
-  float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
-  int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
-  float tminL, tmaxL, tminR, tmaxR;
-  bool goL, goR;
-  if (STATS) cnt->box_tests += 2;
-  if (T.R.fast) {
-    goL = slab<true>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
-    goR = slab<true>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
-  } else {
-    goL = slab<false>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
-    goR = slab<false>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
-  }
-  const float behind = -S.cull_abs;
-  float lim = T.best.k * 1.001f + S.cull_abs;
-  goL = goL && !(tminL > lim) && !(tmaxL < behind);
-  goR = goR && !(tminR > lim) && !(tmaxR < behind);
-  // leaves are tested at once (one triangle each); the nearer one first so that the farther can still be culled
-  bool leafL = goL && refL < 0, leafR = goR && refR < 0;
-  if (leafL || leafR) {
-    bool rightFirst = leafR && (!leafL || tminR < tminL);
-    int t0 = rightFirst ? ~refR : ~refL;
-    if (STATS) cnt->tri_tests++;
-    test_triangle<SMEM>(S, t0, T.R.o, T.R.d, T.best, T.best_rank);
-    lim = T.best.k * 1.001f + S.cull_abs;
-    if (leafL && leafR) {
-      float tOther = rightFirst ? tminL : tminR;
-      if (!(tOther > lim)) {
-        if (STATS) cnt->tri_tests++;
-        test_triangle<SMEM>(S, rightFirst ? ~refL : ~refR, T.R.o, T.R.d, T.best, T.best_rank);
-        lim = T.best.k * 1.001f + S.cull_abs;
-      }
-    }
-    goL = goL && !leafL && !(tminL > lim);
-    goR = goR && !leafR && !(tminR > lim);
-  }
-  if (goL && goR) {
-    bool leftNear = tminL <= tminR;
-    st.base[T.sp * st.stride] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? tminR : tminL);
-    ++T.sp;
-    T.cur = leftNear ? refL : refR;
-  } else if (goL) {
-    T.cur = refL;
-  } else if (goR) {
-    T.cur = refR;
-  } else {
-    bool found = false;
-    while (T.sp > 0) {
-      --T.sp;
-      float2 e = st.base[T.sp * st.stride];
-      if (!(e.y > T.best.k * 1.001f + S.cull_abs)) {
-        T.cur = __float_as_int(e.x);
-        found = true;
-        break;
-      }
-    }
-    T.active = found;
-  }
-}
-
-// Leaves found by a node step are not tested on the spot (only a few lanes of a warp reach a leaf in the
-// same turn) but parked in a four-entry per-lane array in shared memory (entry e of lane l at parks[e * stride]);
-// the warp tests parked triangles together once enough lanes hold one.  Last in, first out; of a pair of
-// leaves the farther is parked first so that the nearer is tested first.
-constexpr int kParkCap = 4;
-
-// both children through the true-division slab test; out of line: only rays with a zero, denormal or huge
-// direction component come here
-// (everything by value so that no caller state is forced into local memory).  Returns (tminL, tminR, goL, goR)
-// with the verdicts as 1.0f / 0.0f and the "wholly behind the origin" cull already applied through `behind`.
-__device__ __noinline__ float4 slab_pair_slow(v3 o, v3 d, float4 q0, float4 q1, float4 q2, float behind) {
-  RayDiv R;
-  R.o = o; R.d = d; R.r = mk3(0.0f, 0.0f, 0.0f); R.fast = false;
-  float tminL, tmaxL, tminR, tmaxR;
-  bool goL = slab<false>(R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
-  bool goR = slab<false>(R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
-  goL = goL && !(tmaxL < behind);
-  goR = goR && !(tmaxR < behind);
-  return make_float4(tminL, tminR, goL ? 1.0f : 0.0f, goR ? 1.0f : 0.0f);
-}
-
-// one node; leaf children that pass their box test are parked instead of tested (needs pn <= kParkCap - 2 on entry)
-template <bool SMEM, bool STATS>
-RT_DEV void trav_step_park(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int pstride, LaneStack st,
-                           TraceCounters *cnt) {
-  const float4 *p = S.nodes + 4 * (size_t)T.cur;
-  float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
+  const float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
   const int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
-  float tminL, tminR;
-  bool goL, goR;
+  float loL, hiL, loR, hiR;
   if (STATS) cnt->box_tests += 2;
-  if (T.R.fast) {
-    float tmaxL, tmaxR;
-    goL = slab<true>(T.R, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
-    goR = slab<true>(T.R, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
-    goL = goL && !(tmaxL < -S.cull_abs);
-    goR = goR && !(tmaxR < -S.cull_abs);
-  } else {
-    float4 r = slab_pair_slow(T.R.o, T.R.d, q0, q1, q2, -S.cull_abs);
-    tminL = r.x; tminR = r.y;
-    goL = r.z != 0.0f; goR = r.w != 0.0f;
-  }
+  slab_cons(T.Q, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &loL, &hiL);
+  slab_cons(T.Q, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &loR, &hiR);
   const float lim = T.best.k * 1.001f + S.cull_abs;
-  goL = goL && !(tminL > lim);
-  goR = goR && !(tminR > lim);
+  const float behind = -S.cull_abs;
+  bool goL = hiL >= loL && !(loL > lim) && !(hiL < behind);
+  bool goR = hiR >= loR && !(loR > lim) && !(hiR < behind);
   const bool leafL = goL && refL < 0, leafR = goR && refR < 0;
   const bool both = leafL && leafR;
   // parked last = tested first: the nearer leaf goes last
-  const bool rightNearer = both ? (tminR < tminL) : leafR;
+  const bool rightNearer = both ? (loR < loL) : leafR;
   const int nearerTri = rightNearer ? ~refR : ~refL;
   const int fartherTri = rightNearer ? ~refL : ~refR;
   if (both) { parks[pn * pstride] = (uint32_t)fartherTri; ++pn; }
   if (leafL || leafR) { parks[pn * pstride] = (uint32_t)nearerTri; ++pn; }
   goL = goL && !leafL;
   goR = goR && !leafR;
-  const bool leftNear = tminL <= tminR;
+  const bool leftNear = loL <= loR;
   if (goL && goR) {
-    st.base[T.sp * st.stride] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? tminR : tminL);
+    st.base[T.sp * st.stride] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? loR : loL);
     ++T.sp;
     T.cur = leftNear ? refL : refR;
   } else if (goL || goR) {
@@ -426,7 +356,7 @@ RT_DEV void trav_step_park(const SceneView &S, Trav &T, int &pn, uint32_t *parks
     bool found = false;
     while (T.sp > 0) {
       --T.sp;
-      float2 e = st.base[T.sp * st.stride];
+      const float2 e = st.base[T.sp * st.stride];
       if (!(e.y > lim)) {
         T.cur = __float_as_int(e.x);
         found = true;
@@ -437,15 +367,37 @@ RT_DEV void trav_step_park(const SceneView &S, Trav &T, int &pn, uint32_t *parks
   }
 }
 
+// the whole walk by one thread (k_primary, k_trace_rays, verify mode); `parks` = kParkCap words of this thread
+template <bool SMEM, bool STATS>
+RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, uint32_t *parks, int pstride,
+                            TraceCounters *cnt) {
+  if (!ray_is_fast(S, o, d)) return closest_hit_exact<SMEM>(S, o, d);
+  Trav T;
+  int pn = 0;
+  trav_begin<SMEM, STATS>(S, T, o, d, pn, parks, cnt);
+  while (T.active || pn > 0) {
+    if (pn > 0 && (!T.active || pn > kParkCap - 2)) {
+      --pn;
+      if (STATS) cnt->tri_tests++;
+      test_triangle<SMEM>(S, (int)parks[pn * pstride], o, d, T.best, T.best_rank);
+    } else {
+      trav_step<SMEM, STATS>(S, T, pn, parks, pstride, st, cnt);
+    }
+  }
+  if (T.best.tri >= 0 && !validate_hit(S, o, d, T.best.tri)) return closest_hit_exact<SMEM>(S, o, d);
+  return T.best;
+}
+
 // TRAV: 0 fast, 1 reference, 2 verify (both; keeps reference, counts disagreements)
 template <int TRAV, bool SMEM, bool STATS>
-RT_DEV Hit closest_hit(const SceneView &S, v3 o, v3 d, LaneStack st, TraceCounters *cnt, unsigned int *mismatch) {
-  if (TRAV == 0) return closest_hit_fast<SMEM, STATS>(S, o, d, st, cnt);
+RT_DEV Hit closest_hit(const SceneView &S, v3 o, v3 d, LaneStack st, uint32_t *parks, int pstride, TraceCounters *cnt,
+                       unsigned int *mismatch) {
+  if (TRAV == 0) return closest_hit_fast<SMEM, STATS>(S, o, d, st, parks, pstride, cnt);
   if (TRAV == 1) return closest_hit_reference<SMEM, STATS>(S, o, d, cnt);
   Hit a = closest_hit_reference<SMEM, STATS>(S, o, d, cnt);
   TraceCounters dummy;
   dummy.box_tests = 0; dummy.tri_tests = 0;
-  Hit b = closest_hit_fast<SMEM, false>(S, o, d, st, &dummy);
+  Hit b = closest_hit_fast<SMEM, false>(S, o, d, st, parks, pstride, &dummy);
   if (a.tri != b.tri || __float_as_int(a.k) != __float_as_int(b.k)) (*mismatch)++;
   return a;
 }

@@ -35,7 +35,8 @@ typedef enum {
 #define B200RT_RNG_PHILOX 1    /* counter-based Philox4x32-10, counter = (pixel, sample, bounce, n), key = seed */
 
 /* traversal modes — both return the hit the reference's rayTrace (MathLib.cl:234-288) returns */
-#define B200RT_TRAVERSAL_FAST 0      /* front-to-back, distance-culled, ties resolved by the reference's visiting rank */
+#define B200RT_TRAVERSAL_FAST 0      /* front-to-back, conservatively culled, winner validated by the exact leaf-box test;
+                                        ties resolved by the reference's visiting rank */
 #define B200RT_TRAVERSAL_REFERENCE 1 /* the reference's visiting order incl. its capped stack (stack.cl:21-26) */
 #define B200RT_TRAVERSAL_VERIFY 2    /* runs both per ray, counts disagreements in stats.mismatches, keeps REFERENCE */
 
@@ -64,7 +65,7 @@ typedef struct {
   uint64_t mismatches;  /* TRAVERSAL_VERIFY only */
   uint64_t samples;     /* pixel-samples evaluated */
   float primary_ms;     /* device time of the primary-hit kernel (CUDA events) */
-  float trace_ms;       /* device time of the path-tracing kernel */
+  float trace_ms;       /* device time of the wavefront iterations (all k_shade + k_trace launches) */
   float total_ms;       /* first launch to last launch of the call, device time */
   float upload_ms;      /* host->device copies of the call (wall clock) */
   int32_t kernel_launches; /* kernels launched by the last call */
@@ -72,7 +73,8 @@ typedef struct {
   int32_t triangles;
   int32_t bvh_depth;
   int32_t scene_in_smem;  /* 1 when the repacked scene is staged in shared memory */
-  int32_t reserved[3];
+  int32_t revalidated;    /* rays whose fast-traversal winner failed the exact leaf-box test and were re-traced exactly */
+  int32_t reserved[2];
 } b200rt_stats;
 
 void b200rt_default_opts(b200rt_opts *opts);
@@ -143,8 +145,7 @@ int b200rt_img_processing(b200rt_ctx *ctx, const float *src, float *dst, int64_t
 int b200rt_get_stats(const b200rt_ctx *ctx, b200rt_stats *stats);
 
 /* Device math used by the kernels, exposed so tests can compare it value by value with the oracle:
- * fn 0 sin, 1 cos, 2 acos, 3 asin, 4 atan2(a,b), 5 tan, 6 pow(a,b), 7 a/b through the traversal's
- * reciprocal+FMA division, 8 sqrt. */
+ * fn 0 sin, 1 cos, 2 acos, 3 asin, 4 atan2(a,b), 5 tan, 6 pow(a,b), 7 a/b, 8 sqrt, 9/10 sincos. */
 int b200rt_math_probe(b200rt_ctx *ctx, int fn, const float *a, const float *b, int64_t n, float *out);
 
 /* Philox4x32-10 block of the device implementation (known-answer tests). */

@@ -56,26 +56,16 @@ def test_atan2_pow_sqrt(gpu_ctx):
     assert np.array_equal(bits(gpu_ctx.math_probe(8, x)), bits(np.sqrt(x)))
 
 
-def test_reciprocal_fma_division_is_ieee_division(gpu_ctx):
-    """div_by(): x * RN(1/d) + two FMA corrections must equal IEEE x / d for every operand the slab test
-    can see (|d| in [2^-40, 2^40]; outside that range the kernel uses true division anyway)."""
+def test_division_probe_is_ieee(gpu_ctx):
+    """fn 7 = the division the exact slab test uses (__fdiv_rn)."""
     r = np.random.default_rng(2)
-    n = 1 << 22
+    n = 1 << 20
     a = (r.standard_normal(n) * 10.0 ** r.uniform(-8, 8, n)).astype(np.float32)
     b = (r.standard_normal(n) * 10.0 ** r.uniform(-11, 11, n)).astype(np.float32)
-    a[:6] = [0.0, -0.0, 1.0, -1.0, 3.0, 16777215.0]
-    b[:6] = [3.0, 7.0, 3.0, 3.0, 0.0, 16777213.0]
     got = gpu_ctx.math_probe(7, a, b)
     with np.errstate(all="ignore"):
         want = (a / b).astype(np.float32)
-    same = (bits(got) == bits(want)) | ((got == 0) & (want == 0)) | (np.isnan(got) & np.isnan(want))
-    assert same.all(), f"{(~same).sum()} quotients differ"
-    # adversarial mantissas: numerators/denominators near powers of two and all-ones patterns
-    m = np.array([0x3f800000, 0x3f800001, 0x3fffffff, 0x3f7fffff, 0x40000001, 0x3fc00000, 0x3faaaaab, 0x3f000001],
-                 dtype=np.uint32).view(np.float32)
-    a2, b2 = np.meshgrid(m, m)
-    got = gpu_ctx.math_probe(7, a2.ravel(), b2.ravel())
-    assert np.array_equal(bits(got), bits((a2.ravel() / b2.ravel()).astype(np.float32)))
+    assert np.array_equal(bits(got), bits(want))
 
 
 def test_philox_known_answers(gpu_ctx):
@@ -146,6 +136,33 @@ def test_arbitrary_rays_all_traversals(gpu_ctx):
     gpu_ctx.trace_rays(rays, rt.make_opts(traversal=rt.TRAVERSAL_REFERENCE, collect_stats=True))
     st = gpu_ctx.stats()
     assert (st["box_tests"], st["tri_tests"]) == (cnt["box_tests"], cnt["tri_tests"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell", "monkey_cfg2", "furnace"])
+def test_grazing_rays_fast_equals_oracle(gpu_ctx, name):
+    """Rays aimed exactly at triangle vertices, edge points and box corners: the cases where Möller–Trumbore and
+    the slab test of a (often zero-thickness) leaf box can disagree within rounding.  The fast traversal must
+    still return the reference's hit (its winner is validated by the exact leaf-box test, rt_trace.cuh)."""
+    sc = fixtures.load_scene(name)
+    fixtures.upload(gpu_ctx, sc)
+    r = np.random.default_rng(11)
+    vp = sc["V_p"].reshape(-1, 3)
+    face = sc["faceData"].reshape(-1, 10)
+    n = 40000
+    t = r.integers(0, face.shape[0], n)
+    a, b, c = vp[face[t, 7]], vp[face[t, 8]], vp[face[t, 9]]
+    w = r.uniform(0, 1, (n, 1)).astype(np.float32)
+    kind = r.integers(0, 3, n)
+    target = np.where((kind == 0)[:, None], a, np.where((kind == 1)[:, None], a + w * (b - a), b + w * (c - b))).astype(np.float32)
+    lo, hi = vp.min(0), vp.max(0)
+    org = r.uniform(lo - 0.5 * (hi - lo), hi + 0.5 * (hi - lo), (n, 3)).astype(np.float32)
+    rays = np.concatenate([org, (target - org).astype(np.float32)], axis=1).astype(np.float32)
+    rays[: n // 4, 3:] /= np.linalg.norm(rays[: n // 4, 3:], axis=1, keepdims=True)  # unit and non-unit directions
+    want_tri, want_k, _ = oracle.trace_rays(sc, rays)
+    tri, k = gpu_ctx.trace_rays(rays, rt.make_opts(traversal=rt.TRAVERSAL_FAST))
+    assert np.array_equal(tri, want_tri), f"{(tri != want_tri).sum()} triangle ids differ"
+    assert np.array_equal(bits(k), bits(want_k))
 
 
 def test_capped_stack_compat_switch(gpu_ctx):

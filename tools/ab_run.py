@@ -30,7 +30,8 @@ def main():
             if best is None or st["total_ms"] < best["total_ms"]:
                 best = st
         print(f"{os.path.basename(sys.argv[1])} {name} {w}x{h} spp{spp}: rays {best['rays']} total {best['total_ms']:.2f} ms "
-              f"{best['rays'] / best['total_ms'] / 1e3:.1f} Mrays/s mean {float(out.mean()):.6f}", flush=True)
+              f"{best['rays'] / best['total_ms'] / 1e3:.1f} Mrays/s mean {float(out.mean()):.6f} primary {best['primary_ms']:.2f} ms "
+              f"launches {best['kernel_launches']} reval {best.get('revalidated')}", flush=True)
 
 
 if __name__ == "__main__":
