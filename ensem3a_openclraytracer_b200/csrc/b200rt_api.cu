@@ -22,6 +22,8 @@ namespace {
 
 thread_local std::string g_create_error;
 
+constexpr size_t kSmemSceneMax = 48 * 1024;  // repacked nodes + triangles up to this size are staged in shared memory
+
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
@@ -42,7 +44,7 @@ struct b200rt_ctx {
   bool have_scene = false;
   bool have_scene_cached = false;  // scene_hash / ibl_hash are valid
   uint64_t scene_hash = 0, mat_hash = 0;
-  DevBuf d_nodes, d_tris, d_normals, d_tboxes, d_mats, d_bvh9;
+  DevBuf d_nodes, d_tris, d_normals, d_tboxes, d_frames, d_mats, d_bvh9;
   int n_nodes9 = 0, n_inner = 0, n_tris = 0, n_mats = 0;
   int depth = 0, ref_stack_need = 0;
   bool canonical = true;
@@ -51,7 +53,7 @@ struct b200rt_ctx {
   float cull_abs = 0.0f, cmax = 0.0f;
   int fast_ok = 1;
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
-  int quorum = 16, refill_min = 8, tri_quorum = 16, steps_per_turn = 2;
+  int quorum = 16, refill_min = 8, tri_quorum = 16;
   std::vector<int32_t> tri_mat;  // for re-validating material edits
 
   // environment map
@@ -162,9 +164,9 @@ void frame_setup(const b200rt_ctx *c, const float *cam, const float *env, int wi
   F->key1 = (uint32_t)(o.seed >> 32);
 }
 
-size_t scene_smem_bytes(const b200rt_ctx *c) { return (size_t)c->n_inner * 64 + (size_t)c->n_tris * 48; }
+size_t scene_smem_bytes(const b200rt_ctx *c) { return (size_t)c->n_inner * 80 + (size_t)c->n_tris * 48; }
 
-bool use_smem_scene(const b200rt_ctx *c) { return scene_smem_bytes(c) <= 48 * 1024; }
+bool use_smem_scene(const b200rt_ctx *c) { return scene_smem_bytes(c) <= kSmemSceneMax; }
 
 size_t smem_bytes(const b200rt_ctx *c, bool smem_scene) {
   return lane_smem_bytes(c->depth + 2) + (smem_scene ? scene_smem_bytes(c) : 0);
@@ -174,9 +176,11 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   A->F = F;
   SceneView &S = A->S;
   S.nodes = static_cast<const float4 *>(c->d_nodes.p);
+  S.node_f4 = use_smem_scene(c) ? 5 : 4;
   S.tris = static_cast<const float4 *>(c->d_tris.p);
   S.normals = static_cast<const float4 *>(c->d_normals.p);
   S.tboxes = static_cast<const float4 *>(c->d_tboxes.p);
+  S.frames = static_cast<const float4 *>(c->d_frames.p);
   S.mats = static_cast<const float *>(c->d_mats.p);
   S.bvh9 = static_cast<const float *>(c->d_bvh9.p);
   S.root_ref = c->root_ref;
@@ -208,7 +212,6 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   A->quorum = c->quorum;
   A->refill_min = c->refill_min;
   A->tri_quorum = c->tri_quorum;
-  A->steps_per_turn = c->steps_per_turn;
   A->validate = 0;
 }
 
@@ -476,7 +479,6 @@ int b200rt_create(int device, b200rt_ctx **out) {
   };
   env_int("B200RT_QUORUM", 1, 32, &c->quorum);
   env_int("B200RT_REFILL_MIN", 1, 32, &c->refill_min);
-  env_int("B200RT_STEPS", 1, 16, &c->steps_per_turn);
   env_int("B200RT_TRI_QUORUM", 1, 32, &c->tri_quorum);
   auto bail = [&](const char *what, cudaError_t err) {
     fail(nullptr, B200RT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
@@ -497,7 +499,7 @@ void b200rt_destroy(b200rt_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_mats, &c->d_bvh9, &c->d_prim_dirk,
+  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_frames, &c->d_mats, &c->d_bvh9, &c->d_prim_dirk,
                     &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b, &c->d_pA, &c->d_pB, &c->d_pC,
                     &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt};
   for (DevBuf *b : bufs)
@@ -676,7 +678,9 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
           }
       }
       n_inner = (int)order.size();
-      nodes.resize((size_t)n_inner * 4);
+      // small scenes are staged in shared memory with 80-byte node spacing (SceneView::node_f4)
+      const size_t nf4 = ((size_t)n_inner * 80 + (size_t)n_tris * 48 <= kSmemSceneMax) ? 5 : 4;
+      nodes.assign((size_t)n_inner * nf4, make_float4(0, 0, 0, 0));
       for (int q = 0; q < n_inner; ++q) {
         int cur = order[q];
         int l = L(cur), r = R(cur);
@@ -686,10 +690,10 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
         float fl, fr;
         memcpy(&fl, &refl, 4);
         memcpy(&fr, &refr, 4);
-        nodes[4 * (size_t)q + 0] = make_float4(bl[2], bl[3], bl[4], bl[5]);
-        nodes[4 * (size_t)q + 1] = make_float4(bl[6], bl[7], br[2], br[3]);
-        nodes[4 * (size_t)q + 2] = make_float4(br[4], br[5], br[6], br[7]);
-        nodes[4 * (size_t)q + 3] = make_float4(fl, fr, 0.0f, 0.0f);
+        nodes[nf4 * (size_t)q + 0] = make_float4(bl[2], bl[3], bl[4], bl[5]);
+        nodes[nf4 * (size_t)q + 1] = make_float4(bl[6], bl[7], br[2], br[3]);
+        nodes[nf4 * (size_t)q + 2] = make_float4(br[4], br[5], br[6], br[7]);
+        nodes[nf4 * (size_t)q + 3] = make_float4(fl, fr, 0.0f, 0.0f);
       }
     }
   }
@@ -708,6 +712,7 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   if (ensure(c, c->d_tris, tris.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_normals, normals.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_tboxes, tboxes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_frames, (size_t)n_tris * kFrameVec * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_nodes, nodes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_bvh9, (size_t)n_bvh * 4)) return B200RT_ERR_CUDA;
   CU(cudaMemcpyAsync(c->d_tris.p, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -716,6 +721,9 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   if (!nodes.empty())
     CU(cudaMemcpyAsync(c->d_nodes.p, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_bvh9.p, bvh, (size_t)n_bvh * 4, cudaMemcpyHostToDevice, c->stream));
+  k_tri_frames<<<(n_tris + 127) / 128, 128, 0, c->stream>>>(static_cast<const float4 *>(c->d_normals.p), n_tris,
+                                                           static_cast<float4 *>(c->d_frames.p));
+  CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   c->n_nodes9 = n_nodes;
   c->n_inner = n_inner;

@@ -50,10 +50,9 @@ struct KernelArgs {
   int stack_depth;        // entries per lane
   int n_work;             // work items (32-pixel tiles x 32)
   int tiles_x;
-  int quorum;             // k_trace: parked leaves are flushed / lanes refilled when fewer lanes than this can step
+  int quorum;             // k_trace: the node phase ends when fewer lanes than this can step
   int refill_min;         // idle lanes pull new rays once this many are idle
-  int tri_quorum;         // parked triangles are tested once this many lanes hold one
-  int steps_per_turn;     // node steps between two looks at the warp's state
+  int tri_quorum;         // the leaf phase repeats while at least this many lanes hold a parked leaf
   int validate;           // 1: hits come from the conservative traversal and must pass validate_hit
 };
 
@@ -80,7 +79,7 @@ RT_DEV SceneView stage_scene(const KernelArgs &A, unsigned char *smem, size_t *u
     return S;
   }
   __shared__ __align__(8) uint64_t bar;
-  const uint32_t nb = (uint32_t)A.n_nodes * 64u, tb = (uint32_t)A.n_tris * 48u;
+  const uint32_t nb = (uint32_t)A.n_nodes * 16u * (uint32_t)A.S.node_f4, tb = (uint32_t)A.n_tris * 48u;
   float4 *s_nodes = reinterpret_cast<float4 *>(smem);
   float4 *s_tris = reinterpret_cast<float4 *>(smem + nb);
   if (threadIdx.x == 0) {
@@ -221,6 +220,9 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
 }
 
 // ---- shading ----------------------------------------------------------------------------------------------------
+// The per-path state machine is written as a sequence of phases with the warp re-converged between them, so that
+// e.g. the direction sampling runs once per warp for every lane that needs it, whichever way the lane got there
+// (bounce hit, or sample ended and the next one starts from the cached primary hit).
 __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ KernelArgs A, int iter) {
   const FrameParams &F = A.F;
   const SceneView &S = A.S;
@@ -234,136 +236,160 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ K
   const unsigned int warps = (gridDim.x * kShadeBlock) >> 5;
   for (unsigned int tb = ((blockIdx.x * kShadeBlock + threadIdx.x) >> 5) << 5; tb < n_in; tb += warps << 5) {
     const unsigned int t = tb + lane;
-    bool alive = false;
+    const bool valid = t < n_in;
+    // ---- phase 0: load -------------------------------------------------------------------------------------------
     int pix = 0;
-    if (t < n_in) {
+    uint32_t meta = 1u;
+    rng_state g;
+    g.a = 0u;
+    v3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(0.0f, 0.0f, 1.0f), acc = mk3(1.0f, 1.0f, 1.0f);
+    float hk = 0.0f;
+    int htri = -1;
+    if (valid) {
       pix = list_in[t];
-      const float4 sa = A.pA[pix], sb = A.pB[pix];
-      const uint32_t meta = __float_as_uint(sb.z);
-      rng_state g;
+      const float4 sb = A.pB[pix];
+      meta = __float_as_uint(sb.z);
       g.a = __float_as_uint(sb.w);
-      const bool first = (meta & 1u) != 0u;
-      int sun_ray = (int)((meta >> 3) & 1u), seg_type = (int)((meta >> 4) & 15u);
-      int j = (int)((meta >> 8) & 255u), s = (int)(meta >> 16);
-      v3 o = mk3(sa.x, sa.y, sa.z);
-      v3 d = mk3(sa.w, sb.x, sb.y);
-      v3 acc = mk3(1.0f, 1.0f, 1.0f);
-      float hk = 0.0f;
-      int htri = -1;
-      bool pixel_done = false, start = first, shade = false;
-
-      if (!first) {  // ---- resolve the ray traced in the previous iteration
-        const float4 sc = A.pC[pix];
-        acc = mk3(sc.x, sc.y, sc.z);
+      if (!(meta & 1u)) {
+        const float4 sa = A.pA[pix], sc = A.pC[pix];
         const int2 hh = A.pHit[pix];
+        o = mk3(sa.x, sa.y, sa.z);
+        d = mk3(sa.w, sb.x, sb.y);
+        acc = mk3(sc.x, sc.y, sc.z);
         htri = hh.x;
         hk = __int_as_float(hh.y);
-        if (A.validate && htri >= 0) {
-          const v3 dray = sun_ray ? F.sun_dir : d;
-          if (!validate_hit(S, o, dray, htri)) {  // grazing ray: the conservative walk's winner is not a candidate
-            const Hit h = closest_hit_exact<false>(S, o, dray);
-            htri = h.tri;
-            hk = h.k;
-            ++reval;
-          }
-        }
-        bool end_sample = false;
-        if (!sun_ray) {
-          if (htri >= 0) {  // the bounce ray becomes the current segment (:91-93)
-            const int mat = __float_as_int(__ldg(S.tris + 3 * (size_t)htri + 2).y);
-            const Material mb = load_material(S.mats, mat);
-            if (mb.type != 0) {
-              if (j == F.max_bounce) {  // :99-103
-                acc = mk3(0.0f, 0.0f, 0.0f);
-                end_sample = true;
-              } else {
-                ++j;
-                shade = true;
-              }
-            } else {  // :105-109
-              acc = acc * mb.roughness;
+      }
+    }
+    const bool first = (meta & 1u) != 0u;
+    int sun_ray = (int)((meta >> 3) & 1u), seg_type = (int)((meta >> 4) & 15u);
+    int j = (int)((meta >> 8) & 255u), s = (int)(meta >> 16);
+    bool pixel_done = false, start = valid && first, shade = false, end_sample = false, sun_done = false;
+
+    // ---- phase 1: the winner of the conservative walk must pass the exact leaf-box test ---------------------------------
+    if (valid && !first && A.validate && htri >= 0) {
+      const v3 dray = sun_ray ? F.sun_dir : d;
+      if (!validate_hit(S, o, dray, htri)) {  // grazing ray: re-trace exactly
+        const Hit h = closest_hit_exact<false>(S, o, dray);
+        htri = h.tri;
+        hk = h.k;
+        ++reval;
+      }
+    }
+    __syncwarp();
+
+    // ---- phase 2: resolve the traced ray (Raytracing.cl:91-137) ------------------------------------------------------------
+    if (valid && !first) {
+      if (!sun_ray) {
+        if (htri >= 0) {  // the bounce ray becomes the current segment (:91-93)
+          const int mat = __float_as_int(__ldg(S.tris + 3 * (size_t)htri + 2).y);
+          const Material mb = load_material(S.mats, mat);
+          if (mb.type != 0) {
+            if (j == F.max_bounce) {  // :99-103
+              acc = mk3(0.0f, 0.0f, 0.0f);
               end_sample = true;
+            } else {
+              ++j;
+              shade = true;
             }
-          } else {  // escaped: shadow ray towards the sun from the same origin (:115-124); d keeps the escaped direction
-            sun_ray = 1;
+          } else {  // :105-109
+            acc = acc * mb.roughness;
+            end_sample = true;
           }
-        } else {  // sun ray finished, :125-137
-          v3 sun = mk3(0.0f, 0.0f, 0.0f);
-          if (htri < 0) {
-            if (seg_type != 3) sun = mk3(F.sun_power, F.sun_power, F.sun_power);
-          } else {
-            const int mat = __float_as_int(__ldg(S.tris + 3 * (size_t)htri + 2).y);
-            const Material ms = load_material(S.mats, mat);
-            if (ms.type == 3) sun = ms.color * F.sun_power;
-          }
-          const v3 envl = ibl_lookup(F, A.ibl, d) * F.ibl_power;
-          acc = acc * (sun + envl);
-          end_sample = true;
+        } else {  // escaped: shadow ray towards the sun from the same origin (:115-124); d keeps the escaped direction
+          sun_ray = 1;
         }
-        if (end_sample) {
-          float *acc_px = A.out + 3 * (size_t)pix;
-          v3 sum = mk3(acc_px[0], acc_px[1], acc_px[2]);
-          sum = sum + acc;  // :207
-          ++s;
-          ++samples;
-          if (s >= F.s1) {
-            write_pixel(A, pix, sum);
-            pixel_done = true;
-          } else {
-            acc_px[0] = sum.x; acc_px[1] = sum.y; acc_px[2] = sum.z;
-            start = true;
-          }
-        }
+      } else {
+        sun_done = true;
       }
-
-      if (start) {  // ---- reload the cached primary hit (Raytracing.cl:195-201)
-        const float4 dk = A.prim_dirk[pix];
-        o = F.cam_pos;
-        d = mk3(dk.x, dk.y, dk.z);
-        hk = dk.w;
-        htri = A.prim_tri[pix];
-        acc = mk3(1.0f, 1.0f, 1.0f);
-        j = 0;
-        shade = true;
+    }
+    __syncwarp();
+    if (sun_done) {  // sun ray finished, :125-137
+      v3 sun = mk3(0.0f, 0.0f, 0.0f);
+      if (htri < 0) {
+        if (seg_type != 3) sun = mk3(F.sun_power, F.sun_power, F.sun_power);
+      } else {
+        const int mat = __float_as_int(__ldg(S.tris + 3 * (size_t)htri + 2).y);
+        const Material ms = load_material(S.mats, mat);
+        if (ms.type == 3) sun = ms.color * F.sun_power;
       }
+      v3 envl;
+      if (F.ibl_power == 0.0f) {
+        // texel/255 is a finite value >= 0, so texel/255 * 0 is a zero of ibl_power's sign whatever the texel
+        envl = mk3(0.5f * F.ibl_power, 0.5f * F.ibl_power, 0.5f * F.ibl_power);
+      } else {
+        envl = ibl_lookup(F, A.ibl, d) * F.ibl_power;
+      }
+      acc = acc * (sun + envl);
+      end_sample = true;
+    }
+    __syncwarp();
+    if (end_sample) {
+      float *acc_px = A.out + 3 * (size_t)pix;
+      v3 sum = mk3(acc_px[0], acc_px[1], acc_px[2]);
+      sum = sum + acc;  // :207
+      ++s;
+      ++samples;
+      if (s >= F.s1) {
+        write_pixel(A, pix, sum);
+        pixel_done = true;
+      } else {
+        acc_px[0] = sum.x; acc_px[1] = sum.y; acc_px[2] = sum.z;
+        start = true;
+      }
+    }
+    // ---- phase 3: a new sample starts from the cached primary hit (Raytracing.cl:195-201) --------------------------------------
+    if (start) {
+      const float4 dk = A.prim_dirk[pix];
+      o = F.cam_pos;
+      d = mk3(dk.x, dk.y, dk.z);
+      hk = dk.w;
+      htri = A.prim_tri[pix];
+      acc = mk3(1.0f, 1.0f, 1.0f);
+      j = 0;
+      shade = true;
+    }
+    __syncwarp();
 
-      if (shade) {  // ---- next direction, BRDF * cos / pdf (:51-87); segment = (o, d, hk, htri)
-        const float4 t2 = __ldg(S.tris + 3 * (size_t)htri + 2);
-        const float4 nn = __ldg(S.normals + htri);
-        const v3 n = mk3(nn.x, nn.y, nn.z);
-        const Material m = load_material(S.mats, __float_as_int(t2.y));
-        v3 nd, brdf;
-        float inv_pdf;
-        if (m.type == 3) {
-          nd = d;
-          brdf = m.color;
-          inv_pdf = 1.0f / fabsf(dot(nd, unit(n)));
+    // ---- phase 4: next direction, BRDF * cos / pdf (:51-87); segment = (o, d, hk, htri) ------------------------------------------
+    if (shade) {
+      const float4 t2 = __ldg(S.tris + 3 * (size_t)htri + 2);
+      const float4 nn = __ldg(S.normals + htri);
+      const v3 n = mk3(nn.x, nn.y, nn.z);
+      const Material m = load_material(S.mats, __float_as_int(t2.y));
+      const TriFrame tf = load_tri_frame(S.frames, htri, m.type == 3 ? 0 : (m.type == 1 ? 1 : 2));
+      v3 nd, brdf;
+      float inv_pdf;
+      if (m.type == 3) {
+        nd = d;
+        brdf = m.color;
+        inv_pdf = 1.0f / fabsf(dot(nd, tf.un));
+      } else {
+        float u0, u1;
+        if (F.rng_mode == 0) draw2<0>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
+        else draw2<1>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
+        if (m.type == 1) {
+          nd = sample_cosine(n, tf, u0, u1, &inv_pdf);
+          brdf = m.color * (1.0f / 3.14f);
         } else {
-          float u0, u1;
-          if (F.rng_mode == 0) draw2<0>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
-          else draw2<1>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &u0, &u1);
-          if (m.type == 1) {
-            nd = sample_cosine(n, u0, u1, &inv_pdf);
-            brdf = m.color * (1.0f / 3.14f);
-          } else {
-            nd = sample_uniform(n, u0, u1, &inv_pdf);
-            brdf = bsdf_ggx(m, neg3(d), nd, n);
-          }
+          nd = sample_uniform(n, tf, u0, u1, &inv_pdf);
+          brdf = bsdf_ggx(m, neg3(d), nd, n);
         }
-        o = o + unit(d) * hk;  // :79 — no offset along the normal
-        d = nd;
-        const float att = inv_pdf * fabsf(dot(nd, unit(n)));
-        acc = (acc * brdf) * att;
-        seg_type = m.type;
-        sun_ray = 0;
       }
+      o = o + unit(d) * hk;  // :79 — no offset along the normal
+      d = nd;
+      const float att = inv_pdf * fabsf(dot(nd, tf.un));
+      acc = (acc * brdf) * att;
+      seg_type = m.type;
+      sun_ray = 0;
+    }
+    __syncwarp();
 
-      if (!pixel_done) {
-        A.pA[pix] = make_float4(o.x, o.y, o.z, d.x);
-        A.pB[pix] = make_float4(d.y, d.z, __uint_as_float(meta_pack(0, sun_ray, seg_type, j, s)), __uint_as_float(g.a));
-        A.pC[pix] = make_float4(acc.x, acc.y, acc.z, 0.0f);
-        alive = true;
-      }
+    // ---- phase 5: store, join the next list -----------------------------------------------------------------------------------------
+    const bool alive = valid && !pixel_done;
+    if (alive) {
+      A.pA[pix] = make_float4(o.x, o.y, o.z, d.x);
+      A.pB[pix] = make_float4(d.y, d.z, __uint_as_float(meta_pack(0, sun_ray, seg_type, j, s)), __uint_as_float(g.a));
+      A.pC[pix] = make_float4(acc.x, acc.y, acc.z, 0.0f);
     }
     const unsigned int m = __ballot_sync(0xffffffffu, alive);
     if (m != 0u) {
@@ -382,6 +408,16 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ K
     if (samples) atomicAdd(&A.counters->samples, samples);
     if (reval) atomicAdd(&A.counters->revalidated, (unsigned long long)reval);
   }
+}
+
+// per-triangle sampling frames, once per scene upload
+__global__ void k_tri_frames(const float4 *__restrict__ normals, int n_tris, float4 *__restrict__ frames) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tris) return;
+  const float4 nn = normals[t];
+  float4 f[kFrameVec];
+  make_tri_frame(mk3(nn.x, nn.y, nn.z), f);
+  for (int k = 0; k < kFrameVec; ++k) frames[(size_t)kFrameVec * t + k] = f[k];
 }
 
 // ---- tracing ------------------------------------------------------------------------------------------------------
@@ -416,40 +452,41 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
   TraceCounters tc;
   tc.box_tests = 0; tc.tri_tests = 0;
 
+  int thresh = A.quorum;  // the node phase runs while at least this many lanes can step
   for (;;) {
-    const bool can_node = T.active && pn <= kParkCap - 2;
-    const unsigned int nodem = __ballot_sync(0xffffffffu, can_node);
-    const unsigned int parkm = __ballot_sync(0xffffffffu, pn > 0);
-    const int n_node = __popc(nodem), n_park = __popc(parkm);
-    // ---- parked triangles: one round, every lane that holds one tests its most recent -----------------------------
-    if (n_park >= A.tri_quorum || (n_park > 0 && n_node < A.quorum)) {
+    // ---- node phase: one node per lane per turn -----------------------------------------------------------------------------
+    for (;;) {
+      const bool can = T.active && pn <= kParkCap - 2;
+      if (__popc(__ballot_sync(0xffffffffu, can)) < thresh) break;
+      if (can) trav_step<SMEM, STATS>(S, T, pn, parks, kBlock, st, &tc);
+    }
+    // ---- leaf phase: every lane that holds a parked leaf tests its most recent; again while many lanes hold one -------------
+    for (unsigned int pm = __ballot_sync(0xffffffffu, pn > 0); pm != 0u;) {
       if (pn > 0) {
         --pn;
         if (STATS) tc.tri_tests++;
         test_triangle<SMEM>(S, (int)parks[pn * kBlock], T.o, T.d, T.best, T.best_rank);
       }
+      pm = __ballot_sync(0xffffffffu, pn > 0);
+      if (__popc(pm) < A.tri_quorum) break;
+    }
+    // ---- finished rays are handed back; idle lanes pull the next rays together ---------------------------------------------------
+    const bool finished = (path >= 0) && !T.active && pn == 0;
+    if (finished) {
+      A.pHit[path] = make_int2(T.best.tri, __float_as_int(T.best.k));
+      path = -1;
+    }
+    const unsigned int idle = __ballot_sync(0xffffffffu, path < 0);
+    if (exhausted) {
+      if (idle == 0xffffffffu) break;
       continue;
     }
-    // ---- finished rays are handed back; idle lanes pull the next rays together ---------------------------------------
-    const bool finished = (path >= 0) && !T.active && pn == 0;
-    const unsigned int finm = __ballot_sync(0xffffffffu, finished);
-    const unsigned int holdm = __ballot_sync(0xffffffffu, path >= 0);
-    const unsigned int idle = ~holdm | finm;
     const int n_idle = __popc(idle);
-    if (exhausted) {
-      if (finm != 0u) {
-        if (finished) {
-          A.pHit[path] = make_int2(T.best.tri, __float_as_int(T.best.k));
-          path = -1;
-        }
-        continue;
-      }
-      if (holdm == 0u) break;
-    } else if (n_idle > 0 && (n_idle >= A.refill_min || n_node < A.quorum)) {
-      if (finished) {
-        A.pHit[path] = make_int2(T.best.tri, __float_as_int(T.best.k));
-        path = -1;
-      }
+    if (n_idle == 0) continue;
+    if (n_idle < A.refill_min &&
+        __popc(__ballot_sync(0xffffffffu, T.active && pn <= kParkCap - 2)) >= A.quorum)
+      continue;  // enough lanes can still step: let more finish before paying for a refill
+    {
       int need = n_idle;
       int rank = __popc(idle & lt_mask);
       bool want = path < 0;
@@ -458,7 +495,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
           unsigned int b = 0;
           if (lane == 0) b = atomicAdd(wc, kChunk);
           b = __shfl_sync(0xffffffffu, b, 0);
-          if (b >= n) { exhausted = true; break; }
+          if (b >= n) { exhausted = true; thresh = 1; break; }
           c_next = b;
           c_end = min(b + kChunk, n);
         }
@@ -482,14 +519,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
         c_next += take;
         need -= take;
       }
-      continue;
     }
-    // ---- node steps --------------------------------------------------------------------------------------------------------
-    // Here at least one lane can step: a lane that holds an unfinished ray is either steppable or holds a parked
-    // leaf, and parked leaves with fewer than `quorum` steppable lanes were flushed above.
-    if (n_node == 0) break;  // unreachable; never spin
-    for (int it = 0; it < A.steps_per_turn; ++it)
-      if (T.active && pn <= kParkCap - 2) trav_step<SMEM, STATS>(S, T, pn, parks, kBlock, st, &tc);
   }
 
   for (int o = 16; o > 0; o >>= 1) {

@@ -105,13 +105,6 @@ RT_HD v3 apply_rotor(const rotor &r, v3 v) {
   return mk3(o.x, o.y, o.z);
 }
 
-RT_DEV v3 rotate_about(float angle, v3 axis, v3 v) {
-  float s, c;
-  cr_sincos(angle * 0.5f, &s, &c);
-  rotor r = make_rotor(c, s, axis);
-  return apply_rotor(r, v);
-}
-
 // ---- random numbers ---------------------------------------------------------------------------
 RT_HD float bits_to_unit(uint32_t bits) {  // MathLib.cl:302-309
 #ifdef __CUDA_ARCH__

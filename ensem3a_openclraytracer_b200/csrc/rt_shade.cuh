@@ -69,38 +69,72 @@ RT_DEV v3 ibl_lookup(const FrameParams &F, cudaTextureObject_t tex, v3 dir) {
   return mk3(__fdiv_rn((float)t.x, 255.0f), __fdiv_rn((float)t.y, 255.0f), __fdiv_rn((float)t.z, 255.0f)) * 1.0f;
 }
 
-// frame that takes the local +Z hemisphere onto normal n — shared by both samplers
-// (MathLib.cl:325-336 and :349-361).  normalise_axis: the uniform sampler normalises the axis before
-// rotateVec (which normalises again), the cosine sampler does not.
-RT_DEV v3 to_world(v3 local, v3 n, bool normalise_axis) {
+// ---- per-triangle sampling frame ------------------------------------------------------------------------------
+// Both samplers rotate a local +Z hemisphere direction onto the triangle's normal n (MathLib.cl:325-336 and
+// :349-361): angle acos(n.z) about cross((0,0,1), n), through rotateVec — or, when |normalize(n).z| == 1, scale by
+// n.z.  All of it depends on the triangle alone, so k_tri_frames evaluates it once per triangle at upload time with
+// exactly the device code a per-sample evaluation would run:
+//   f0 = normalize(n).xyz, z-aligned flag      f1,f2 = rotor of the cosine sampler (axis not normalised before
+//   rotateVec)      f3,f4 = rotor of the uniform sampler (axis normalised first; rotateVec normalises again)
+constexpr int kFrameVec = 5;  // float4 per triangle
+
+struct TriFrame {
+  v3 un;
+  bool zal;
+  rotor rot;
+};
+
+RT_DEV void make_tri_frame(v3 n, float4 *f) {
   const v3 zup = mk3(0.0f, 0.0f, 1.0f);
-  if (fabsf(dot(unit(n), zup)) == 1.0f) return local * n.z;
-  v3 axis = cross(zup, n);
-  if (normalise_axis) axis = unit(axis);
-  float ang = cr_acos(dot(n, zup));
-  return rotate_about(ang, axis, local);
+  const v3 un = unit(n);
+  const bool zal = fabsf(dot(un, zup)) == 1.0f;
+  const v3 axis = cross(zup, n);
+  const float ang = cr_acos(dot(n, zup));
+  float s, c;
+  cr_sincos(ang * 0.5f, &s, &c);
+  const rotor rc = make_rotor(c, s, axis);
+  const rotor ru = make_rotor(c, s, unit(axis));
+  f[0] = make_float4(un.x, un.y, un.z, zal ? 1.0f : 0.0f);
+  f[1] = make_float4(rc.q.w, rc.q.x, rc.q.y, rc.q.z);
+  f[2] = make_float4(rc.qi.w, rc.qi.x, rc.qi.y, rc.qi.z);
+  f[3] = make_float4(ru.q.w, ru.q.x, ru.q.y, ru.q.z);
+  f[4] = make_float4(ru.qi.w, ru.qi.x, ru.qi.y, ru.qi.z);
+}
+
+// which: 0 = unit normal only (glass), 1 = + cosine rotor, 2 = + uniform rotor
+RT_DEV TriFrame load_tri_frame(const float4 *frames, int tri, int which) {
+  const float4 *f = frames + (size_t)kFrameVec * tri;
+  TriFrame T;
+  const float4 f0 = __ldg(f);
+  T.un = mk3(f0.x, f0.y, f0.z);
+  T.zal = f0.w != 0.0f;
+  if (which != 0) {
+    const float4 a = __ldg(f + (which == 1 ? 1 : 3)), b = __ldg(f + (which == 1 ? 2 : 4));
+    T.rot.q.w = a.x; T.rot.q.x = a.y; T.rot.q.y = a.z; T.rot.q.z = a.w;
+    T.rot.qi.w = b.x; T.rot.qi.x = b.y; T.rot.qi.y = b.z; T.rot.qi.z = b.w;
+  }
+  return T;
 }
 
 // MathLib.cl:313-339
-RT_DEV v3 sample_cosine(v3 n, float u, float u2, float *inv_pdf) {
+RT_DEV v3 sample_cosine(v3 n, const TriFrame &T, float u, float u2, float *inv_pdf) {
   float theta = u2 * 2.0f * 3.14f;
   float rad = sqrtf(u);
   float st, ct;
   cr_sincos(theta, &st, &ct);
   v3 local = mk3(rad * ct, rad * st, sqrtf(fmaxf(0.0f, 1.0f - u)));
-  const v3 zup = mk3(0.0f, 0.0f, 1.0f);
   v3 l;
-  if (fabsf(dot(unit(n), zup)) == 1.0f) {
+  if (T.zal) {
     l = local * n.z;
   } else {
-    l = unit(to_world(local, n, false));
+    l = unit(apply_rotor(T.rot, local));
   }
   *inv_pdf = 3.14f / fmaxf(dot(l, n), 0.0f);
   return l;
 }
 
 // MathLib.cl:342-366
-RT_DEV v3 sample_uniform(v3 n, float u, float u2, float *inv_pdf) {
+RT_DEV v3 sample_uniform(v3 n, const TriFrame &T, float u, float u2, float *inv_pdf) {
   float phi = 2.0f * 3.14f * u;
   float theta = cr_acos(1.0f - u2);
   float st, ct, sp, cp;
@@ -108,7 +142,8 @@ RT_DEV v3 sample_uniform(v3 n, float u, float u2, float *inv_pdf) {
   cr_sincos(phi, &sp, &cp);
   v3 local = mk3(cp * st, st * sp, ct);
   *inv_pdf = 2.0f * 3.14f;
-  return to_world(local, n, true);
+  if (T.zal) return local * n.z;
+  return apply_rotor(T.rot, local);
 }
 
 RT_DEV float ipow(float x, int n) {  // pown: repeated multiply from 1

@@ -37,7 +37,8 @@
 namespace b200rt {
 
 // ---- repacked scene -------------------------------------------------------------------------------
-// node (64 B, 4 x float4), interior nodes only, root = 0:
+// node (4 x float4; 64 B apart in global memory, 80 B apart when the scene is staged in shared memory so that
+// lanes reading different nodes spread over all 32 banks), interior nodes only, breadth-first, root = 0:
 //   q0 = Lmin.x Lmin.y Lmin.z Lmax.x
 //   q1 = Lmax.y Lmax.z Rmin.x Rmin.y
 //   q2 = Rmin.z Rmax.x Rmax.y Rmax.z
@@ -49,9 +50,11 @@ namespace b200rt {
 // leaf box (32 B, 2 x float4): min.xyz -, max.xyz -   of the leaf that holds the triangle (validate_hit).
 struct SceneView {
   const float4 *nodes;
+  int node_f4;              // float4 per node: 4, or 5 for a scene small enough to be staged in shared memory
   const float4 *tris;
   const float4 *normals;
   const float4 *tboxes;
+  const float4 *frames;     // kFrameVec float4 per triangle (rt_shade.cuh)
   const float *mats;        // 6 floats per material
   // as-is reference buffers for closest_hit_reference
   const float *bvh9;
@@ -242,7 +245,7 @@ __device__ __noinline__ Hit closest_hit_exact(const SceneView &S, v3 o, v3 d) {
   const float behind = -S.cull_abs;
   int cur = 0, sp = 0;
   for (;;) {
-    const float4 *p = S.nodes + 4 * (size_t)cur;
+    const float4 *p = S.nodes + (size_t)S.node_f4 * cur;
     float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
     int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
     float tminL, tmaxL, tminR, tmaxR;
@@ -324,7 +327,7 @@ RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, int &pn, uint32_
 template <bool SMEM, bool STATS>
 RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int pstride, LaneStack st,
                       TraceCounters *cnt) {
-  const float4 *p = S.nodes + 4 * (size_t)T.cur;
+  const float4 *p = S.nodes + (size_t)S.node_f4 * T.cur;
   const float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
   const int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
   float loL, hiL, loR, hiR;
