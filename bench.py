@@ -14,10 +14,12 @@ reference's own FileManager/BVH.py (tests/golden/make_golden.py).
 value      Mrays/s, device time (CUDA events on the launching stream), inputs resident in HBM.
 e2e        the same metric through the reference-facing call with HOST buffers: every step re-uploads
            scene + environment (caches invalidated), renders, and reads the image back.
-roofline   HBM-style: algorithmic bytes of SURVEY.md §8d (36 B per box test + 136 B per triangle test of
-           the REFERENCE traversal, + material / texel / output bytes) per second over the measured HBM peak.
+roofline   dominant kernel = k_trace (one launch per wavefront iteration).  HBM-style: algorithmic bytes of
+           SURVEY.md §8d (36 B per box test + 136 B per triangle test of the REFERENCE traversal, + material
+           bytes) of the rays the k_trace launches of one step process, over the summed duration of those
+           launches (CUDA events around every launch, one extra profiled step), against the measured HBM peak.
            The scene is cache-resident by design, so this is a traffic-equivalent, not DRAM traffic
-           (DESIGN.md "Rooflines"); `traffic` is the ncu-measured DRAM bytes of the same launch.
+           (DESIGN.md §4); `traffic` is the ncu-measured DRAM bytes of one mid-frame k_trace launch.
 cpu_baseline  oracle/_ref (the reference's .cl compiled by g++) on the host cores, bounded sample.
 """
 import argparse
@@ -201,7 +203,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ensem3a_openclraytracer_b200 as rt
-    from ensem3a_openclraytracer_b200.multigpu import DistributedRenderer
+    from ensem3a_openclraytracer_b200.multigpu import DistributedRenderer, split_range
 
     torch.cuda.set_device(local)
     if world > 1:
@@ -271,7 +273,19 @@ def main():
     ms_total, rays_step = float(t.item()), float(r.item())
     ms_per_step = ms_total / args.steps
     mrays = rays_step / ms_per_step / 1e3
-    trace_ms_last = st["trace_ms"]
+    launches_step = st["kernel_launches"]
+
+    # ---- one profiled step: CUDA events around every k_shade / k_trace launch (roofline of the dominant kernel) -----
+    if dr is None:
+        ctx.render_device(cam, env, W, H, spp, mb, out_dev.data_ptr(),
+                          rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=WORKLOAD["seed"], time_kernels=True))
+    else:
+        s0, s1 = split_range(spp, world)[rank]
+        ctx.render_device(cam, env, W, H, spp, mb, out_dev.data_ptr(),
+                          rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=WORKLOAD["seed"], time_kernels=True,
+                                       output=rt.OUT_SUMS, sample_begin=s0, sample_end=s1))
+    barrier()
+    stp = ctx.stats()
 
     # ---- end to end through the plugin with host buffers ---------------------------------------------------------
     host_out = np.zeros(npix * 3, np.float32)
@@ -312,12 +326,14 @@ def main():
         return
 
     peak, peak_src = measured_peak()
-    achieved = rays_step * bytes_per_ray / (ms_per_step * 1e-3) / 1e9
+    n_trace = (launches_step - 1) // 2                      # k_primary + (n_iter + 1) k_shade + n_iter k_trace
+    trace_rays = stp["rays"] - W * H                        # rank 0's rays minus the primary rays of k_primary
+    achieved = trace_rays * bytes_per_ray / (stp["trace_kernel_ms"] * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("k_paths_dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get("k_trace_dram_bytes_per_launch")
         except Exception:
             traffic = None
     line = {
@@ -326,18 +342,23 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME, "width": W, "height": H, "spp": spp, "max_bounce": mb,
                    "rng": "philox4x32-10 keyed (pixel,sample,bounce)", "traversal": "fast",
+                   "pipeline": "k_primary, then (spp*(maxBounce+2)) x (k_shade, k_trace) wavefront iterations",
                    "partition": "sample ranges" if world > 1 else "single GPU", "reduce": args.reduce if world > 1 else None,
                    "l2": "256 MiB flush write between timed iterations", "scene_in_smem": bool(st["scene_in_smem"])},
         "samples_per_s": npix * spp / (ms_per_step * 1e-3),
         "rays_per_step": rays_step, "rays_per_sample": rays_step / (npix * spp),
         "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * float(te.item()) / e2e_steps, "steps": e2e_steps},
-        "gpu_launches": args.steps * (2 + (1 if world > 1 else 0)),
+        "gpu_launches": args.steps * (launches_step + (1 if world > 1 else 0)),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray,
                      "box_tests_per_ray_reference": box_per_ray, "tri_tests_per_ray_reference": tri_per_ray,
-                     "kernel": "k_paths", "kernel_ms_last_step": trace_ms_last,
+                     "kernel": "k_trace", "launches_per_step": n_trace,
+                     "avg_launch_us": 1e3 * stp["trace_kernel_ms"] / max(n_trace, 1),
+                     "kernel_ms_per_step": stp["trace_kernel_ms"], "k_shade_ms_per_step": stp["shade_kernel_ms"],
+                     "k_primary_ms_per_step": stp["primary_ms"], "step_ms_profiled": stp["total_ms"],
+                     "share_of_step": stp["trace_kernel_ms"] / stp["total_ms"],
                      "note": "algorithmic bytes in the reference's layout; the 2 MB scene is cache-resident"},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -26,7 +26,7 @@ class Opts(ctypes.Structure):
     _fields_ = [("rng_mode", ctypes.c_int32), ("traversal", ctypes.c_int32), ("stack_cap", ctypes.c_int32),
                 ("output", ctypes.c_int32), ("sample_begin", ctypes.c_int32), ("sample_end", ctypes.c_int32),
                 ("pixel_begin", ctypes.c_int32), ("pixel_end", ctypes.c_int32), ("seed", ctypes.c_uint64),
-                ("collect_stats", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5)]
+                ("collect_stats", ctypes.c_int32), ("time_kernels", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
 
 
 class Stats(ctypes.Structure):
@@ -35,7 +35,7 @@ class Stats(ctypes.Structure):
                 ("trace_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("upload_ms", ctypes.c_float),
                 ("kernel_launches", ctypes.c_int32), ("nodes", ctypes.c_int32), ("triangles", ctypes.c_int32),
                 ("bvh_depth", ctypes.c_int32), ("scene_in_smem", ctypes.c_int32), ("revalidated", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 2)]
+                ("shade_kernel_ms", ctypes.c_float), ("trace_kernel_ms", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -120,12 +120,13 @@ def _i32(a):
 
 
 def make_opts(rng_mode=RNG_REFERENCE, traversal=TRAVERSAL_FAST, stack_cap=20, output=OUT_FINAL, sample_begin=0,
-              sample_end=0, pixel_begin=0, pixel_end=0, seed=0, collect_stats=False):
+              sample_end=0, pixel_begin=0, pixel_end=0, seed=0, collect_stats=False, time_kernels=False):
     o = Opts()
     o.rng_mode, o.traversal, o.stack_cap, o.output = rng_mode, traversal, stack_cap, output
     o.sample_begin, o.sample_end, o.pixel_begin, o.pixel_end = sample_begin, sample_end, pixel_begin, pixel_end
     o.seed = seed & 0xFFFFFFFFFFFFFFFF
     o.collect_stats = 1 if collect_stats else 0
+    o.time_kernels = 1 if time_kernels else 0
     return o
 
 

@@ -36,6 +36,8 @@ struct b200rt_ctx {
   cudaStream_t stream = nullptr;      // stream in use
   cudaStream_t own_stream = nullptr;  // created by b200rt_create
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> kev;  // per-launch events of the last time_kernels render
+  int kev_used = 0;
   std::string err;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -53,7 +55,7 @@ struct b200rt_ctx {
   float cull_abs = 0.0f, cmax = 0.0f;
   int fast_ok = 1;
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
-  int quorum = 16, refill_min = 8, tri_quorum = 16;
+  int quorum = 16, refill_min = 8, tri_quorum = 8;
   std::vector<int32_t> tri_mat;  // for re-validating material edits
 
   // environment map
@@ -340,6 +342,12 @@ int read_counters(b200rt_ctx *c) {
   if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->stats.primary_ms = ms;
   if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->stats.trace_ms = ms;
   if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]) == cudaSuccess) c->stats.total_ms = ms;
+  c->stats.shade_kernel_ms = 0.0f;
+  c->stats.trace_kernel_ms = 0.0f;
+  for (int i = 0; i + 1 < c->kev_used; ++i)  // event i sits before launch i; launches alternate shade, trace, shade, ...
+    if (cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]) == cudaSuccess)
+      ((i & 1) ? c->stats.trace_kernel_ms : c->stats.shade_kernel_ms) += ms;
+  c->kev_used = 0;
   c->stats_pending = false;
   return 0;
 }
@@ -420,8 +428,19 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   rc = launch_primary(c, A, trav, smem, false, o.collect_stats != 0, nullptr, nullptr);
   if (rc) return rc;
   CU(cudaEventRecord(c->ev[1], c->stream));
+  c->kev_used = 0;
+  if (o.time_kernels) {
+    const size_t need = 2 * (size_t)n_iter + 2;
+    while (c->kev.size() < need) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      c->kev.push_back(e);
+    }
+  }
   for (int it = 0; it <= n_iter; ++it) {
+    if (o.time_kernels) CU(cudaEventRecord(c->kev[c->kev_used++], c->stream));
     k_shade<<<wl.shade_grid, kShadeBlock, 0, c->stream>>>(A, it);
+    if (o.time_kernels) CU(cudaEventRecord(c->kev[c->kev_used++], c->stream));
     if (it < n_iter) wl.trace<<<wl.trace_grid, kBlock, wl.trace_smem, c->stream>>>(A, it);
   }
   CU(cudaGetLastError());
@@ -509,6 +528,7 @@ void b200rt_destroy(b200rt_ctx *c) {
   if (c->d_counters) cudaFree(c->d_counters);
   for (int i = 0; i < 3; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }

@@ -81,6 +81,23 @@ RT_DEV float4 ld4(const float4 *p) {
   return __ldg(p);
 }
 
+// One node = 64 contiguous bytes.  From global memory it is fetched with two 256-bit loads (LDG.E.256, sm_100+):
+// lanes of a warp sit at unrelated nodes, so the L1 cost of a node visit is one wavefront per lane per load
+// instruction, and two loads instead of four halve it.
+template <bool SMEM>
+RT_DEV void ld_node(const float4 *p, float4 &q0, float4 &q1, float4 &q2, float4 &q3) {
+  if (SMEM) {
+    q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
+  } else {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w)
+        : "l"(p));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w)
+        : "l"(p + 2));
+  }
+}
+
 // ---- exact slab test, MathLib.cl:169-188 --------------------------------------------------------------
 RT_DEV bool slab_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float *tmin,
                        float *tmax) {
@@ -328,7 +345,8 @@ template <bool SMEM, bool STATS>
 RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int pstride, LaneStack st,
                       TraceCounters *cnt) {
   const float4 *p = S.nodes + (size_t)S.node_f4 * T.cur;
-  const float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
+  float4 q0, q1, q2, q3;
+  ld_node<SMEM>(p, q0, q1, q2, q3);
   const int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
   float loL, hiL, loR, hiR;
   if (STATS) cnt->box_tests += 2;

@@ -55,7 +55,9 @@ typedef struct {
   int32_t pixel_end;
   uint64_t seed;         /* Philox key */
   int32_t collect_stats; /* 1: also count box / triangle tests (slower) */
-  int32_t reserved[5];
+  int32_t time_kernels;  /* 1: bracket every k_shade / k_trace launch with CUDA events and report the sums
+                            (stats.shade_kernel_ms / trace_kernel_ms); adds two event records per iteration */
+  int32_t reserved[4];
 } b200rt_opts;
 
 typedef struct {
@@ -74,7 +76,8 @@ typedef struct {
   int32_t bvh_depth;
   int32_t scene_in_smem;  /* 1 when the repacked scene is staged in shared memory */
   int32_t revalidated;    /* rays whose fast-traversal winner failed the exact leaf-box test and were re-traced exactly */
-  int32_t reserved[2];
+  float shade_kernel_ms;  /* only with time_kernels: summed device time of the k_shade launches */
+  float trace_kernel_ms;  /* only with time_kernels: summed device time of the k_trace launches */
 } b200rt_stats;
 
 void b200rt_default_opts(b200rt_opts *opts);
