@@ -774,26 +774,35 @@ int b200rt_set_ibl(b200rt_ctx *c, const uint8_t *rgba, int width, int height) {
   uint64_t h = hash_bytes(rgba, (size_t)width * height * 4, 0x69626cull);
   if (c->have_ibl && c->ibl_hash != 0 && h == c->ibl_hash && width == c->ibl_w && height == c->ibl_h) return 0;
   CU(cudaSetDevice(c->device));
-  CU(cudaStreamSynchronize(c->stream));
-  if (c->ibl_tex) { cudaDestroyTextureObject(c->ibl_tex); c->ibl_tex = 0; }
-  if (c->ibl_array) { cudaFreeArray(c->ibl_array); c->ibl_array = nullptr; }
-  c->have_ibl = false;
-  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-  CU(cudaMallocArray(&c->ibl_array, &fmt, (size_t)width, (size_t)height));
-  CU(cudaMemcpy2DToArrayAsync(c->ibl_array, 0, 0, rgba, (size_t)width * 4, (size_t)width * 4, (size_t)height,
-                              cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  cudaResourceDesc res;
-  memset(&res, 0, sizeof res);
-  res.resType = cudaResourceTypeArray;
-  res.res.array.array = c->ibl_array;
-  cudaTextureDesc td;
-  memset(&td, 0, sizeof td);
-  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;  // CLK_ADDRESS_CLAMP_TO_EDGE (Raytracing.cl:179)
-  td.filterMode = cudaFilterModePoint;                          // integer coordinates address single texels
-  td.readMode = cudaReadModeElementType;                        // raw bytes; the kernel divides by 255 itself
-  td.normalizedCoords = 0;                                      // CLK_NORMALIZED_COORDS_FALSE
-  CU(cudaCreateTextureObject(&c->ibl_tex, &res, &td, nullptr));
+  if (c->ibl_array && c->ibl_tex && width == c->ibl_w && height == c->ibl_h) {
+    // same shape: refill the existing array (allocating / freeing device memory synchronises the whole device,
+    // peers and collectives included)
+    c->have_ibl = false;
+    CU(cudaMemcpy2DToArrayAsync(c->ibl_array, 0, 0, rgba, (size_t)width * 4, (size_t)width * 4, (size_t)height,
+                                cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  } else {
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->ibl_tex) { cudaDestroyTextureObject(c->ibl_tex); c->ibl_tex = 0; }
+    if (c->ibl_array) { cudaFreeArray(c->ibl_array); c->ibl_array = nullptr; }
+    c->have_ibl = false;
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    CU(cudaMallocArray(&c->ibl_array, &fmt, (size_t)width, (size_t)height));
+    CU(cudaMemcpy2DToArrayAsync(c->ibl_array, 0, 0, rgba, (size_t)width * 4, (size_t)width * 4, (size_t)height,
+                                cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof res);
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = c->ibl_array;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;  // CLK_ADDRESS_CLAMP_TO_EDGE (Raytracing.cl:179)
+    td.filterMode = cudaFilterModePoint;                          // integer coordinates address single texels
+    td.readMode = cudaReadModeElementType;                        // raw bytes; the kernel divides by 255 itself
+    td.normalizedCoords = 0;                                      // CLK_NORMALIZED_COORDS_FALSE
+    CU(cudaCreateTextureObject(&c->ibl_tex, &res, &td, nullptr));
+  }
   c->ibl_w = width;
   c->ibl_h = height;
   c->ibl_hash = h;
