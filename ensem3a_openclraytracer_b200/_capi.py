@@ -48,7 +48,7 @@ SYMBOLS = [
     "b200rt_reduce_finalize_device", "b200rt_sync", "b200rt_set_stream", "b200rt_invalidate", "b200rt_primary_hits", "b200rt_trace_rays",
     "b200rt_img_processing", "b200rt_get_stats", "b200rt_math_probe", "b200rt_philox_probe", "b200rt_alloc",
     "b200rt_free", "b200rt_ipc_export",
-    "b200rt_ipc_open", "b200rt_ipc_close", "b200rt_version",
+    "b200rt_ipc_open", "b200rt_ipc_close", "b200rt_build_bvh", "b200rt_version",
 ]
 
 _lib = None
@@ -99,6 +99,7 @@ def load_library():
     lib.b200rt_ipc_export.argtypes = [vp, vp, vp]
     lib.b200rt_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
     lib.b200rt_ipc_close.argtypes = [vp, vp]
+    lib.b200rt_build_bvh.argtypes = [vp, i64, vp, i64, vp, i64, ctypes.POINTER(ctypes.c_int32)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("b200rt_version", "b200rt_last_error", "b200rt_default_opts", "b200rt_destroy"):
@@ -128,6 +129,21 @@ def make_opts(rng_mode=RNG_REFERENCE, traversal=TRAVERSAL_FAST, stack_cap=20, ou
     o.collect_stats = 1 if collect_stats else 0
     o.time_kernels = 1 if time_kernels else 0
     return o
+
+
+def build_bvh(face_data, vertex_p, return_depth=False):
+    """BVH.py's exportArray (float32, 9 per node) for the given faceData / V_p, built natively (host cores)."""
+    lib = load_library()
+    face, vp_ = _i32(face_data), _f32(vertex_p)
+    if face.size == 0 or face.size % 10:
+        raise B200RTError("faceData must hold 10 ints per triangle")
+    out = np.empty((2 * (face.size // 10) - 1) * 9, dtype=np.float32)
+    depth = ctypes.c_int32(0)
+    rc = lib.b200rt_build_bvh(_ptr(vp_), vp_.size, _ptr(face), face.size, _ptr(out), out.size, ctypes.byref(depth))
+    if rc != 0:
+        raise B200RTError(f"b200rt_build_bvh failed ({rc}): malformed buffers, more than 2^23 triangles, or a node whose "
+                          "centroids all fall on one side of their mean (BVH.py does not terminate on such input)")
+    return (out, depth.value) if return_depth else out
 
 
 class Context:

@@ -166,6 +166,14 @@ int b200rt_ipc_export(b200rt_ctx *ctx, const void *d_ptr, uint8_t handle_out[64]
 int b200rt_ipc_open(b200rt_ctx *ctx, const uint8_t handle[64], void **d_ptr_out);
 int b200rt_ipc_close(b200rt_ctx *ctx, void *d_ptr);
 
+/* The reference's BVH.py, node for node, on the host cores (no context, no GPU involved): same splits (axis of
+ * largest centroid variance, at the centroid mean, float64, NumPy's summation order), same node numbering, same
+ * float32 boxes, same 9-float export (BVH.py:73-113,147-191).  Replaces `BVH(faceData, V_p).exportArray`
+ * (FileManager.py:245).  bvh_out must hold (2 * n_triangles - 1) * 9 floats.  Returns B200RT_ERR_INVALID for an
+ * input on which BVH.py itself does not terminate (every centroid of some node on one side of its mean). */
+int b200rt_build_bvh(const float *vertex_p, int64_t n_vertex_p, const int32_t *face_data, int64_t n_face_data,
+                     float *bvh_out, int64_t n_bvh_out, int32_t *depth_out);
+
 const char *b200rt_version(void);
 
 #ifdef __cplusplus
