@@ -266,11 +266,12 @@ def main():
     st = ctx.stats()
     rays_local = st["rays"]                 # last step, this rank
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    r = torch.tensor([float(rays_local)], dtype=torch.float64, device=dev)
+    # every rank traces the frame's W*H primary rays (the cached primary hit); they count once for the job
+    r = torch.tensor([float(rays_local - npix)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-    ms_total, rays_step = float(t.item()), float(r.item())
+    ms_total, rays_step = float(t.item()), float(r.item()) + npix
     ms_per_step = ms_total / args.steps
     mrays = rays_step / ms_per_step / 1e3
     launches_step = st["kernel_launches"]
