@@ -86,13 +86,13 @@ def math_checks(ctx):
     g = ctx.math_probe(6, a, b)
     c = oracle.math_probe("pow", a, b)
     emit(kind="math", fn="pow2.2", n=n, mismatches=int((g.view(np.uint32) != c.view(np.uint32)).sum()))
-    # division through reciprocal + FMA correction vs IEEE division
+    # the division of the exact slab test vs IEEE division
     a = (rng.standard_normal(n) * 10 ** rng.uniform(-6, 6, n)).astype(np.float32)
     b = (rng.standard_normal(n) * 10 ** rng.uniform(-6, 6, n)).astype(np.float32)
     g = ctx.math_probe(7, a, b)
     with np.errstate(all="ignore"):
         c = (a / b).astype(np.float32)
-    emit(kind="math", fn="div_by", n=n, mismatches=int((g.view(np.uint32) != c.view(np.uint32)).sum()))
+    emit(kind="math", fn="fdiv", n=n, mismatches=int((g.view(np.uint32) != c.view(np.uint32)).sum()))
     for ctr, k0, k1 in (([0, 0, 0, 0], 0, 0), ([0xffffffff] * 4, 0xffffffff, 0xffffffff),
                         ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], 0xa4093822, 0x299f31d0)):
         emit(kind="philox", gpu=[hex(int(v)) for v in ctx.philox_probe(ctr, k0, k1)],
