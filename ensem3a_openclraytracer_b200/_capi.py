@@ -44,7 +44,7 @@ class Stats(ctypes.Structure):
 # every symbol include/b200rt.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "b200rt_default_opts", "b200rt_create", "b200rt_destroy", "b200rt_last_error", "b200rt_set_scene",
-    "b200rt_set_materials", "b200rt_set_ibl", "b200rt_render", "b200rt_render_device", "b200rt_finalize_device",
+    "b200rt_set_materials", "b200rt_set_ibl", "b200rt_render", "b200rt_render_rgb8", "b200rt_render_device", "b200rt_finalize_device",
     "b200rt_reduce_finalize_device", "b200rt_sync", "b200rt_set_stream", "b200rt_invalidate", "b200rt_primary_hits", "b200rt_trace_rays",
     "b200rt_img_processing", "b200rt_get_stats", "b200rt_math_probe", "b200rt_philox_probe", "b200rt_alloc",
     "b200rt_free", "b200rt_ipc_export",
@@ -83,6 +83,7 @@ def load_library():
     lib.b200rt_set_ibl.argtypes = [vp, vp, i32, i32]
     lib.b200rt_render.argtypes = [vp, vp, vp, i32, i32, i32, i32, ctypes.POINTER(Opts), vp]
     lib.b200rt_render_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, ctypes.POINTER(Opts), vp]
+    lib.b200rt_render_rgb8.argtypes = [vp, vp, vp, i32, i32, i32, i32, ctypes.POINTER(Opts), vp]
     lib.b200rt_finalize_device.argtypes = [vp, vp, vp, i64, i32]
     lib.b200rt_reduce_finalize_device.argtypes = [vp, ctypes.POINTER(vp), i32, vp, i64, i32]
     lib.b200rt_sync.argtypes = [vp]
@@ -213,6 +214,15 @@ class Context:
         o = opts if opts is not None else make_opts()
         self._check(self._lib.b200rt_render(self._h, _ptr(cam_), _ptr(env_), int(width), int(height), int(spp),
                                             int(max_bounce), ctypes.byref(o), _ptr(out)), "b200rt_render")
+        return out
+
+    def render_rgb8(self, cam, env, width, height, spp, max_bounce, opts=None):
+        """(height, width, 3) uint8 image, quantised on the device like FileManager.saveImg does on the host."""
+        cam_, env_ = _f32(cam), _f32(env)
+        out = np.zeros((int(height), int(width), 3), dtype=np.uint8)
+        o = opts if opts is not None else make_opts()
+        self._check(self._lib.b200rt_render_rgb8(self._h, _ptr(cam_), _ptr(env_), int(width), int(height), int(spp),
+                                                 int(max_bounce), ctypes.byref(o), _ptr(out)), "b200rt_render_rgb8")
         return out
 
     def render_device(self, cam, env, width, height, spp, max_bounce, d_out_ptr, opts=None):

@@ -364,6 +364,9 @@ int check_frame_args(b200rt_ctx *c, const float *cam, int width, int height, int
                 (double)cam[6], width);
   if (spp <= 0) return fail(c, B200RT_ERR_INVALID, "spp must be positive (got %d)", spp);
   if (max_bounce < 0) return fail(c, B200RT_ERR_INVALID, "maxBounce must be >= 0 (got %d)", max_bounce);
+  // the per-path state packs the sample index into 16 bits and the bounce into 8 (rt_kernels.cuh meta_pack)
+  if (spp > 65535) return fail(c, B200RT_ERR_UNSUPPORTED, "spp %d exceeds 65535 per launch; accumulate several launches with sample ranges", spp);
+  if (max_bounce > 254) return fail(c, B200RT_ERR_UNSUPPORTED, "maxBounce %d exceeds 254", max_bounce);
   if (o.rng_mode != B200RT_RNG_REFERENCE && o.rng_mode != B200RT_RNG_PHILOX)
     return fail(c, B200RT_ERR_INVALID, "bad rng_mode %d", o.rng_mode);
   if (o.traversal < 0 || o.traversal > 2) return fail(c, B200RT_ERR_INVALID, "bad traversal %d", o.traversal);
@@ -705,8 +708,9 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
         int cur = order[q];
         int l = L(cur), r = R(cur);
         const float *bl = bvh + 9 * (size_t)l, *br = bvh + 9 * (size_t)r;
-        int32_t refl = T(l) != -1 ? ~T(l) : inner_id[l];
-        int32_t refr = T(r) != -1 ? ~T(r) : inner_id[r];
+        // interior refs are float4 offsets into the node array (index x floats4-per-node)
+        int32_t refl = T(l) != -1 ? ~T(l) : (int32_t)(inner_id[l] * (int)nf4);
+        int32_t refr = T(r) != -1 ? ~T(r) : (int32_t)(inner_id[r] * (int)nf4);
         float fl, fr;
         memcpy(&fl, &refl, 4);
         memcpy(&fr, &refr, 4);
@@ -830,6 +834,28 @@ int b200rt_render(b200rt_ctx *c, const float *cam, const float *env, int width, 
   int rc = render_impl(c, cam, env, width, height, spp, max_bounce, opts, static_cast<float *>(c->d_out.p));
   if (rc) return rc;
   CU(cudaMemcpyAsync(out, c->d_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));  // blocking read-back, KernelLauncher.py:78
+  CU(cudaStreamSynchronize(c->stream));
+  return read_counters(c);
+}
+
+int b200rt_render_rgb8(b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp, int max_bounce,
+                       const b200rt_opts *opts, uint8_t *out) {
+  if (!c) return B200RT_ERR_INVALID;
+  if (!out) return fail(c, B200RT_ERR_INVALID, "out_rgb8 is NULL");
+  if (width <= 0 || height <= 0) return fail(c, B200RT_ERR_INVALID, "bad frame size %d x %d", width, height);
+  if (opts && opts->output != B200RT_OUT_FINAL) return fail(c, B200RT_ERR_INVALID, "8-bit output needs B200RT_OUT_FINAL");
+  const size_t n = (size_t)width * height * 3;
+  CU(cudaSetDevice(c->device));
+  if (ensure(c, c->d_out, n * sizeof(float))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tmp_a, n)) return B200RT_ERR_CUDA;
+  CU(cudaMemsetAsync(c->d_out.p, 0, n * sizeof(float), c->stream));
+  int rc = render_impl(c, cam, env, width, height, spp, max_bounce, opts, static_cast<float *>(c->d_out.p));
+  if (rc) return rc;
+  int grid = (int)std::min<long long>(((long long)n + 255) / 256, (long long)c->sm_count * 16);
+  k_quantize8<<<grid, 256, 0, c->stream>>>(static_cast<const float *>(c->d_out.p), static_cast<uint8_t *>(c->d_tmp_a.p), (long long)n);
+  CU(cudaGetLastError());
+  c->stats.kernel_launches++;
+  CU(cudaMemcpyAsync(out, c->d_tmp_a.p, n, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return read_counters(c);
 }

@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
 
   Trav T;
   T.active = false;
-  T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0x7fffffff; T.cur = 0; T.sp = 0;
+  T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0x7fffffff; T.lim = 0.0f; T.cur = 0; T.sp = 0;
   T.o = mk3(0, 0, 0); T.d = mk3(1, 1, 1);
   T.Q.r = mk3(1, 1, 1); T.Q.ca = mk3(0, 0, 0); T.Q.cb = mk3(0, 0, 0);
   int pn = 0;         // parked leaves of this lane
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
       if (pn > 0) {
         --pn;
         if (STATS) tc.tri_tests++;
-        test_triangle<SMEM>(S, (int)parks[pn * kBlock], T.o, T.d, T.best, T.best_rank);
+        test_parked<SMEM>(S, T, parks[pn * kBlock], T.o, T.d);
       }
       pm = __ballot_sync(0xffffffffu, pn > 0);
       if (__popc(pm) < A.tri_quorum) break;
@@ -601,6 +601,14 @@ __global__ void k_reduce_finalize(const __grid_constant__ PartList parts, float 
     for (int r = 1; r < parts.n; ++r) a += parts.p[r][e];
     out[e] = clamp01(a / spp);
   }
+}
+
+// 8-bit image as FileManager.saveImg makes it (FileManager.py:334-338): (data * 255).astype('uint8') — a float32
+// product truncated toward zero; the input is already clamped to [0,1]
+__global__ void k_quantize8(const float *__restrict__ in, uint8_t *__restrict__ out, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (uint8_t)__float2int_rz(in[i] * 255.0f);
 }
 
 // ImgProcessing.cl:1-9

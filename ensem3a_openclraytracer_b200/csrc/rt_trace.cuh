@@ -42,7 +42,8 @@ namespace b200rt {
 //   q0 = Lmin.x Lmin.y Lmin.z Lmax.x
 //   q1 = Lmax.y Lmax.z Rmin.x Rmin.y
 //   q2 = Rmin.z Rmax.x Rmax.y Rmax.z
-//   q3 = refL refR (int bits)  -  -        ref >= 0: interior node index, ref < 0: leaf of triangle ~ref
+//   q3 = refL refR (int bits)  -  -        ref >= 0: float4 offset of an interior node (index x node_f4),
+//                                          ref < 0: leaf of triangle ~ref
 // triangle (48 B, 3 x float4):
 //   t0 = A.x A.y A.z e1.x     t1 = e1.y e1.z e2.x e2.y     t2 = e2.z mat rank -   (mat, rank int bits)
 //   with e1 = B - A, e2 = C - A rounded exactly as MathLib.cl:129-130 rounds them.
@@ -262,7 +263,7 @@ __device__ __noinline__ Hit closest_hit_exact(const SceneView &S, v3 o, v3 d) {
   const float behind = -S.cull_abs;
   int cur = 0, sp = 0;
   for (;;) {
-    const float4 *p = S.nodes + (size_t)S.node_f4 * cur;
+    const float4 *p = S.nodes + cur;
     float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
     int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
     float tminL, tmaxL, tminR, tmaxR;
@@ -310,9 +311,12 @@ struct Trav {
   RayFast Q;
   Hit best;
   int best_rank;
-  int cur, sp;
+  float lim;     // sub-trees whose conservative entry distance exceeds this cannot hold a closer hit
+  int cur, sp;   // cur: float4 offset of the node to visit next
   bool active;
 };
+
+RT_DEV float cull_limit(const SceneView &S, float best_k) { return best_k * 1.001f + S.cull_abs; }
 
 // Leaves whose box passes the conservative test are not tested on the spot (only a few lanes of a warp reach a
 // leaf in the same turn) but parked, at most kParkCap per lane (entry e of lane l at parks[e * stride]); the
@@ -327,6 +331,7 @@ RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, int &pn, uint32_
   T.best.tri = -1;
   T.best.k = 1000.0f;
   T.best_rank = 0x7fffffff;
+  T.lim = cull_limit(S, T.best.k);
   T.cur = 0;
   T.sp = 0;
   float lo, hi;
@@ -334,45 +339,42 @@ RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, int &pn, uint32_
   slab_cons(T.Q, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4], S.root_box[5], &lo, &hi);
   T.active = hi >= lo;
   if (T.active && S.root_ref < 0) {
-    parks[0] = (uint32_t)~S.root_ref;
+    parks[0] = (uint32_t)S.root_ref;
     pn = 1;
     T.active = false;
   }
 }
 
-// one node: both child boxes through the conservative test; leaf children are parked (needs pn <= kParkCap - 2)
+// one node: both child boxes through the conservative test; leaf children are parked as their (negative) refs
+// (needs pn <= kParkCap - 2)
 template <bool SMEM, bool STATS>
 RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int pstride, LaneStack st,
                       TraceCounters *cnt) {
-  const float4 *p = S.nodes + (size_t)S.node_f4 * T.cur;
   float4 q0, q1, q2, q3;
-  ld_node<SMEM>(p, q0, q1, q2, q3);
+  ld_node<SMEM>(S.nodes + T.cur, q0, q1, q2, q3);
   const int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
   float loL, hiL, loR, hiR;
   if (STATS) cnt->box_tests += 2;
   slab_cons(T.Q, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &loL, &hiL);
   slab_cons(T.Q, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &loR, &hiR);
-  const float lim = T.best.k * 1.001f + S.cull_abs;
+  const float lim = T.lim;
   const float behind = -S.cull_abs;
-  bool goL = hiL >= loL && !(loL > lim) && !(hiL < behind);
-  bool goR = hiR >= loR && !(loR > lim) && !(hiR < behind);
+  const bool goL = hiL >= loL && !(loL > lim) && !(hiL < behind);
+  const bool goR = hiR >= loR && !(loR > lim) && !(hiR < behind);
   const bool leafL = goL && refL < 0, leafR = goR && refR < 0;
+  const bool inL = goL && refL >= 0, inR = goR && refR >= 0;
+  // one comparison orders both the leaves (nearer leaf parked last = tested first) and the interior children
+  const bool rNear = loR < loL;
+  const int refNear = rNear ? refR : refL, refFar = rNear ? refL : refR;
   const bool both = leafL && leafR;
-  // parked last = tested first: the nearer leaf goes last
-  const bool rightNearer = both ? (loR < loL) : leafR;
-  const int nearerTri = rightNearer ? ~refR : ~refL;
-  const int fartherTri = rightNearer ? ~refL : ~refR;
-  if (both) { parks[pn * pstride] = (uint32_t)fartherTri; ++pn; }
-  if (leafL || leafR) { parks[pn * pstride] = (uint32_t)nearerTri; ++pn; }
-  goL = goL && !leafL;
-  goR = goR && !leafR;
-  const bool leftNear = loL <= loR;
-  if (goL && goR) {
-    st.base[T.sp * st.stride] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? loR : loL);
+  if (both) { parks[pn * pstride] = (uint32_t)refFar; ++pn; }
+  if (leafL || leafR) { parks[pn * pstride] = (uint32_t)(both ? refNear : (leafR ? refR : refL)); ++pn; }
+  if (inL && inR) {
+    st.base[T.sp * st.stride] = make_float2(__int_as_float(refFar), rNear ? loL : loR);
     ++T.sp;
-    T.cur = leftNear ? refL : refR;
-  } else if (goL || goR) {
-    T.cur = goL ? refL : refR;
+    T.cur = refNear;
+  } else if (inL || inR) {
+    T.cur = inL ? refL : refR;
   } else {
     bool found = false;
     while (T.sp > 0) {
@@ -388,6 +390,13 @@ RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int
   }
 }
 
+// a parked leaf: exact Möller–Trumbore, then the culling limit follows the best hit
+template <bool SMEM>
+RT_DEV void test_parked(const SceneView &S, Trav &T, uint32_t ref, v3 o, v3 d) {
+  test_triangle<SMEM>(S, ~(int)ref, o, d, T.best, T.best_rank);
+  T.lim = cull_limit(S, T.best.k);
+}
+
 // the whole walk by one thread (k_primary, k_trace_rays, verify mode); `parks` = kParkCap words of this thread
 template <bool SMEM, bool STATS>
 RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, uint32_t *parks, int pstride,
@@ -400,7 +409,7 @@ RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, uint32
     if (pn > 0 && (!T.active || pn > kParkCap - 2)) {
       --pn;
       if (STATS) cnt->tri_tests++;
-      test_triangle<SMEM>(S, (int)parks[pn * pstride], o, d, T.best, T.best_rank);
+      test_parked<SMEM>(S, T, parks[pn * pstride], o, d);
     } else {
       trav_step<SMEM, STATS>(S, T, pn, parks, pstride, st, cnt);
     }

@@ -108,6 +108,12 @@ int b200rt_set_ibl(b200rt_ctx *ctx, const uint8_t *rgba, int width, int height);
 int b200rt_render(b200rt_ctx *ctx, const float *cam, const float *env, int width, int height, int spp,
                   int max_bounce, const b200rt_opts *opts, float *out_rgb);
 
+/* Render + the 8-bit conversion of FileManager.saveImg (FileManager.py:334-338: `(data*255).astype('uint8')`, float32
+ * product truncated toward zero) on the device, so that only width*height*3 BYTES cross to the host.  out_rgb8:
+ * width*height*3 bytes on the HOST, row-major RGB — what PIL's Image.fromarray(..., 'RGB') takes. */
+int b200rt_render_rgb8(b200rt_ctx *ctx, const float *cam, const float *env, int width, int height, int spp,
+                       int max_bounce, const b200rt_opts *opts, uint8_t *out_rgb8);
+
 /* Same, but out_rgb is a DEVICE pointer on the context's GPU and the call returns after the kernels
  * are enqueued on the context's stream (b200rt_sync waits).  Used by the multi-GPU path, whose
  * per-GPU partial sums are reduced over NVLink before they ever reach the host. */

@@ -95,6 +95,10 @@ def test_launcher_rejects_bad_inputs(launcher):
                                    cam, env, 16 * 16, 1, 1, ibl)
     with pytest.raises(rt.B200RTError):
         launcher.launch_Raytracing(out, *good, cam, env, 16 * 16, 0, 1, ibl)           # spp = 0
+    with pytest.raises(rt.B200RTError, match="65535"):
+        launcher.launch_Raytracing(out, *good, cam, env, 16 * 16, 70000, 1, ibl)       # sample index would not fit
+    with pytest.raises(rt.B200RTError, match="254"):
+        launcher.launch_Raytracing(out, *good, cam, env, 16 * 16, 1, 300, ibl)
 
 
 def test_material_edit_between_renders(launcher):
@@ -234,3 +238,15 @@ def test_per_kernel_timing_stats(gpu_ctx):
     b = gpu_ctx.render(cam, env, 128, 128, 4, 4)
     assert gpu_ctx.stats()["trace_kernel_ms"] == 0.0
     assert np.array_equal(bits(a), bits(b))
+
+
+def test_rgb8_output_matches_saveimg_conversion(gpu_ctx):
+    """b200rt_render_rgb8 = render + FileManager.saveImg's `(data*255).astype('uint8')` (FileManager.py:334-338)."""
+    sc = fixtures.load_scene("serre")
+    fixtures.upload(gpu_ctx, sc)
+    cam, env = fixtures.cam_env(sc["params"], 96, 64)
+    f = gpu_ctx.render(cam, env, 96, 64, 4, 4)
+    u = gpu_ctx.render_rgb8(cam, env, 96, 64, 4, 4)
+    assert u.shape == (64, 96, 3) and u.dtype == np.uint8
+    assert np.array_equal(u, (f.reshape(64, 96, 3) * 255).astype("uint8"))
+    assert u.max() > 0
