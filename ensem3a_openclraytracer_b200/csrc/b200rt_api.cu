@@ -51,7 +51,7 @@ struct b200rt_ctx {
   int depth = 0, ref_stack_need = 0;
   bool canonical = true;
   int root_ref = 0;
-  float root_box[6] = {0, 0, 0, 0, 0, 0};
+  float root_ch[6] = {0, 0, 0, 0, 0, 0};
   float cull_abs = 0.0f, cmax = 0.0f;
   int fast_ok = 1;
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
@@ -128,6 +128,17 @@ rotor h_rotor(float angle, v3 axis) {
 
 const float kDeg2Rad = 3.14f / 180.0f;
 
+// centre / half extent of [mn, mx] for the conservative slab test: h is rounded up so that, in real arithmetic,
+// c - h <= mn and c + h >= mx (a zero-thickness box keeps h = 0)
+void centre_half(float mn, float mx, float *c_out, float *h_out) {
+  const float c = (float)(0.5 * ((double)mn + (double)mx));
+  const double dh = std::fmax((double)c - (double)mn, (double)mx - (double)c);
+  float h = (float)dh;
+  if ((double)h < dh) h = std::nextafterf(h, INFINITY);
+  *c_out = c;
+  *h_out = h;
+}
+
 // Per-frame constants.  Raytracing.cl:24,27,33-35,115-118 and MathLib.cl:73-74.
 void frame_setup(const b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp,
                  int max_bounce, const b200rt_opts &o, FrameParams *F) {
@@ -186,7 +197,7 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   S.mats = static_cast<const float *>(c->d_mats.p);
   S.bvh9 = static_cast<const float *>(c->d_bvh9.p);
   S.root_ref = c->root_ref;
-  for (int i = 0; i < 6; ++i) S.root_box[i] = c->root_box[i];
+  for (int i = 0; i < 6; ++i) S.root_ch[i] = c->root_ch[i];
   S.cull_abs = c->cull_abs;
   S.cmax = c->cmax;
   int cap = o.stack_cap <= 0 ? 20 : (o.stack_cap > 64 ? 64 : o.stack_cap);
@@ -677,7 +688,7 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
     c->ref_stack_need = (int)max_stack;
   }
   if (!(cmax < INFINITY)) return fail(c, B200RT_ERR_INVALID, "scene contains a non-finite coordinate");
-  if (c->depth + 2 > kExactStack) canonical = false;  // closest_hit_exact's thread-local stack
+  if (c->ref_stack_need > kRefStack) canonical = false;  // closest_hit_nodrop's thread-local stack
 
   // ---- repack interior nodes breadth-first into the 64-byte two-child layout --------------------------------------
   std::vector<float4> nodes;
@@ -714,14 +725,19 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
         float fl, fr;
         memcpy(&fl, &refl, 4);
         memcpy(&fr, &refr, 4);
-        nodes[nf4 * (size_t)q + 0] = make_float4(bl[2], bl[3], bl[4], bl[5]);
-        nodes[nf4 * (size_t)q + 1] = make_float4(bl[6], bl[7], br[2], br[3]);
-        nodes[nf4 * (size_t)q + 2] = make_float4(br[4], br[5], br[6], br[7]);
+        float cl[3], hl[3], cr[3], hr[3];
+        for (int k = 0; k < 3; ++k) {
+          centre_half(bl[2 + k], bl[5 + k], &cl[k], &hl[k]);
+          centre_half(br[2 + k], br[5 + k], &cr[k], &hr[k]);
+        }
+        nodes[nf4 * (size_t)q + 0] = make_float4(cl[0], cl[1], cl[2], hl[0]);
+        nodes[nf4 * (size_t)q + 1] = make_float4(hl[1], hl[2], cr[0], cr[1]);
+        nodes[nf4 * (size_t)q + 2] = make_float4(cr[2], hr[0], hr[1], hr[2]);
         nodes[nf4 * (size_t)q + 3] = make_float4(fl, fr, 0.0f, 0.0f);
       }
     }
   }
-  for (int k = 0; k < 6; ++k) c->root_box[k] = bvh[2 + k];
+  for (int k = 0; k < 3; ++k) centre_half(bvh[2 + k], bvh[5 + k], &c->root_ch[k], &c->root_ch[3 + k]);
   {
     float dx = bvh[5] - bvh[2], dy = bvh[6] - bvh[3], dz = bvh[7] - bvh[4];
     c->cull_abs = 1e-3f * std::sqrt(dx * dx + dy * dy + dz * dz);

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
 // The per-path state machine is written as a sequence of phases with the warp re-converged between them, so that
 // e.g. the direction sampling runs once per warp for every lane that needs it, whichever way the lane got there
 // (bounce hit, or sample ended and the next one starts from the cached primary hit).
-__global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ KernelArgs A, int iter) {
+__global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant__ KernelArgs A, int iter) {
   const FrameParams &F = A.F;
   const SceneView &S = A.S;
   const unsigned int n_in = A.cnt[iter];
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(const __grid_constant__ K
     if (valid && !first && A.validate && htri >= 0) {
       const v3 dray = sun_ray ? F.sun_dir : d;
       if (!validate_hit(S, o, dray, htri)) {  // grazing ray: re-trace exactly
-        const Hit h = closest_hit_exact<false>(S, o, dray);
+        const Hit h = closest_hit_nodrop<false>(S, o, dray);
         htri = h.tri;
         hk = h.k;
         ++reval;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
   T.active = false;
   T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0x7fffffff; T.lim = 0.0f; T.cur = 0; T.sp = 0;
   T.o = mk3(0, 0, 0); T.d = mk3(1, 1, 1);
-  T.Q.r = mk3(1, 1, 1); T.Q.ca = mk3(0, 0, 0); T.Q.cb = mk3(0, 0, 0);
+  T.Q.r = mk3(1, 1, 1); T.Q.kn = mk3(0, 0, 0); T.Q.kf = mk3(0, 0, 0);
   int pn = 0;         // parked leaves of this lane
   int path = -1;      // path whose ray this lane is tracing
   unsigned int c_next = 0, c_end = 0;  // the warp's claimed chunk of the list (uniform)
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
           if (TRAV == 0 && ray_is_fast(S, o, d)) {
             trav_begin<SMEM, STATS>(S, T, o, d, pn, parks, &tc);
           } else {  // reference / verify traversal, or a ray the conservative test is not proven for: whole walk at once
-            T.best = (TRAV == 0) ? closest_hit_exact<SMEM>(S, o, d)
+            T.best = (TRAV == 0) ? closest_hit_nodrop<SMEM>(S, o, d)
                                  : closest_hit<TRAV, SMEM, STATS>(S, o, d, st, parks, kBlock, &tc, &mism);
             T.active = false;
           }

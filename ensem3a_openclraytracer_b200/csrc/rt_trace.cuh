@@ -11,9 +11,8 @@
 // Implementations:
 //   closest_hit_reference  the reference's own visiting order on the as-is 9-float nodes, including its
 //                          capped stack that silently drops pushes (stack.cl:21-26);
-//   closest_hit_exact      front-to-back over the repacked 64-byte two-child nodes with the exact slab test
-//                          at every box (the fallback of the fast path, and the path of rays whose direction
-//                          has a zero / denormal / huge component);
+//   closest_hit_nodrop     the same walk with a stack that never drops (the fallback of the fast path, and the
+//                          path of rays whose direction has a zero / denormal / huge component);
 //   closest_hit_fast       the production path.  It rests on one observation about the reference's slab test:
 //
 //       For a ray whose direction components are all non-zero finite numbers, if a box B' is nested in a
@@ -26,11 +25,12 @@
 //     boxes are nested along every root-to-leaf chain (b200rt_set_scene verifies this; a tree that violates it
 //     is walked by closest_hit_reference).  A triangle is therefore a candidate iff its LEAF box passes the
 //     exact slab test and Möller–Trumbore accepts it; ancestor boxes matter for culling only.  The fast path
-//     walks the tree with a CONSERVATIVE slab test (one FMA per plane, widened by a proven error margin), runs
+//     walks the tree with a CONSERVATIVE slab test (FMAs only, on boxes stored as centre / half-extent and
+//     widened by a proven error margin), runs
 //     the exact Möller–Trumbore on the leaves it reaches, and keeps the best hit; the winner's leaf box is
 //     then put through the exact slab test once (validate_hit).  If it passes — always, except for rays that
 //     graze a box edge within rounding — the winner is the reference's hit: the set searched is a superset of
-//     the candidates and its minimum is a candidate.  If it fails the ray is re-traced by closest_hit_exact.
+//     the candidates and its minimum is a candidate.  If it fails the ray is re-traced by closest_hit_nodrop.
 #pragma once
 #include "rt_math.cuh"
 
@@ -39,9 +39,9 @@ namespace b200rt {
 // ---- repacked scene -------------------------------------------------------------------------------
 // node (4 x float4; 64 B apart in global memory, 80 B apart when the scene is staged in shared memory so that
 // lanes reading different nodes spread over all 32 banks), interior nodes only, breadth-first, root = 0:
-//   q0 = Lmin.x Lmin.y Lmin.z Lmax.x
-//   q1 = Lmax.y Lmax.z Rmin.x Rmin.y
-//   q2 = Rmin.z Rmax.x Rmax.y Rmax.z
+//   q0 = Lc.x Lc.y Lc.z Lh.x        c = box centre, h = half extent, rounded so that [c - h, c + h] encloses
+//   q1 = Lh.y Lh.z Rc.x Rc.y        the child's exact [min, max] (these boxes only cull; exactness lives in the
+//   q2 = Rc.z Rh.x Rh.y Rh.z        leaf boxes of `tboxes` and in the as-is array `bvh9`)
 //   q3 = refL refR (int bits)  -  -        ref >= 0: float4 offset of an interior node (index x node_f4),
 //                                          ref < 0: leaf of triangle ~ref
 // triangle (48 B, 3 x float4):
@@ -60,7 +60,7 @@ struct SceneView {
   // as-is reference buffers for closest_hit_reference
   const float *bvh9;
   int root_ref;             // ~tri when the whole tree is one leaf
-  float root_box[6];        // min xyz, max xyz of node 0
+  float root_ch[6];         // centre xyz, half extent xyz of node 0 (enclosing, like the node records)
   float cull_abs;           // absolute part of the culling margin (1e-3 x scene diagonal)
   float cmax;               // largest |coordinate| of any box plane
   int stack_cap;            // reference traversal
@@ -116,15 +116,20 @@ RT_DEV bool slab_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, f
 }
 
 // ---- conservative slab test ----------------------------------------------------------------------------
-// Per ray: r = RN(1/d) and, per axis, two constants so that for a plane coordinate p
-//     fma(p, r, c_near) <= t_exact(p) <= fma(p, r, c_far),      t_exact(p) = RN(RN(p - o) / d).
-// Error budget, with P = max(|p|, |o|) and u = 2^-24:  t_exact differs from the real (p - o)/d by at most
-// 4u·P|1/d|  (two roundings of a value of magnitude <= 2P/|d|);  fma(p, r, RN(-o·r)) differs from it by at most
-// u·2P|1/d| (r) + u·P|r| (o·r) + u·2P|r| (fma result) + u·P|r| (adding the margin)  < 7u·P|r|.
-// The margin  m = 2^-20 (cmax + |o|) |r| = 16u (cmax + |o|) |r|  covers the sum (11u·P|r|) with room to spare.
-// Valid while every |d| component lies in [2^-40, 2^40] and |o|, cmax <= 2^40 (no overflow, no denormal r).
+// Boxes are held as centre c and half extent h with [c - h, c + h] enclosing the exact [min, max].  Per ray:
+// r = RN(1/d) and two constants per axis, kn = RN(-o·r) - m and kf = RN(-o·r) + m, so that
+//     near = fma(-h, |r|, fma(c, r, kn))  <=  min(t_exact(min), t_exact(max))
+//     far  = fma(+h, |r|, fma(c, r, kf))  >=  max(t_exact(min), t_exact(max)),     t_exact(p) = RN(RN(p - o) / d).
+// Only the FMA pipe is used: no per-axis min / max is needed because |r| orders the two planes; the three
+// `near` values and the three `far` values are then reduced with one 3-input max / min each.
+// Error budget, with P = max(|c| + h, |o|) and u = 2^-24:  t_exact differs from the real (p - o)/d by at most
+// 4u·P|1/d| (two roundings of a value of magnitude <= 2P/|d|);  the FMA chain differs from the real
+// (c -+ h - o)/d by at most  2u·P|r| (r)  +  u·P|r| (o·r)  +  u·(P|r| + m) (kn / kf)  +  2u·P|r| (inner FMA)
+// +  2u·P|r| (outer FMA)  <  9u·P|r|.  The margin  m = 2^-19 (cmax + |o|) |r| = 32u (cmax + |o|) |r|  covers the
+// sum (13u·P|r|) more than twice.  Valid while every |d| component lies in [2^-40, 2^40] and |o|, cmax <= 2^40
+// (no overflow, no denormal r).
 struct RayFast {
-  v3 r, ca, cb;  // ca goes with box.min, cb with box.max
+  v3 r, kn, kf;
 };
 
 RT_DEV bool comp_ok(float d) {
@@ -137,32 +142,34 @@ RT_DEV bool ray_is_fast(const SceneView &S, v3 o, v3 d) {
          fabsf(o.y) <= 1.099511627776e12f && fabsf(o.z) <= 1.099511627776e12f;
 }
 
-RT_DEV void rayfast_axis(float o, float d, float cmax, float *r, float *ca, float *cb) {
+RT_DEV void rayfast_axis(float o, float d, float cmax, float *r, float *kn, float *kf) {
   const float rr = __frcp_rn(d);
   const float t0 = -(o * rr);
-  const float m = (9.5367431640625e-07f /* 2^-20 */ * (cmax + fabsf(o))) * fabsf(rr);
-  const float near = t0 - m, far = t0 + m;
+  const float m = (1.9073486328125e-06f /* 2^-19 */ * (cmax + fabsf(o))) * fabsf(rr);
   *r = rr;
-  *ca = rr > 0.0f ? near : far;   // box.min is the near plane when the ray travels in +axis
-  *cb = rr > 0.0f ? far : near;
+  *kn = t0 - m;
+  *kf = t0 + m;
 }
 
 RT_DEV RayFast make_rayfast(const SceneView &S, v3 o, v3 d) {
   RayFast Q;
-  rayfast_axis(o.x, d.x, S.cmax, &Q.r.x, &Q.ca.x, &Q.cb.x);
-  rayfast_axis(o.y, d.y, S.cmax, &Q.r.y, &Q.ca.y, &Q.cb.y);
-  rayfast_axis(o.z, d.z, S.cmax, &Q.r.z, &Q.ca.z, &Q.cb.z);
+  rayfast_axis(o.x, d.x, S.cmax, &Q.r.x, &Q.kn.x, &Q.kf.x);
+  rayfast_axis(o.y, d.y, S.cmax, &Q.r.y, &Q.kn.y, &Q.kf.y);
+  rayfast_axis(o.z, d.z, S.cmax, &Q.r.z, &Q.kn.z, &Q.kf.z);
   return Q;
 }
 
-// lo <= tmin_exact and hi >= tmax_exact of the same box; the box certainly fails when hi < lo
-RT_DEV void slab_cons(const RayFast &Q, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float *lo,
+// lo <= tmin_exact and hi >= tmax_exact of the box enclosed by (c, h); the box certainly fails when hi < lo
+RT_DEV void slab_cons(const RayFast &Q, float cx, float cy, float cz, float hx, float hy, float hz, float *lo,
                       float *hi) {
-  const float ax = __fmaf_rn(mnx, Q.r.x, Q.ca.x), bx = __fmaf_rn(mxx, Q.r.x, Q.cb.x);
-  const float ay = __fmaf_rn(mny, Q.r.y, Q.ca.y), by = __fmaf_rn(mxy, Q.r.y, Q.cb.y);
-  const float az = __fmaf_rn(mnz, Q.r.z, Q.ca.z), bz = __fmaf_rn(mxz, Q.r.z, Q.cb.z);
-  *lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-  *hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+  const float nx = __fmaf_rn(-hx, fabsf(Q.r.x), __fmaf_rn(cx, Q.r.x, Q.kn.x));
+  const float ny = __fmaf_rn(-hy, fabsf(Q.r.y), __fmaf_rn(cy, Q.r.y, Q.kn.y));
+  const float nz = __fmaf_rn(-hz, fabsf(Q.r.z), __fmaf_rn(cz, Q.r.z, Q.kn.z));
+  const float fx = __fmaf_rn(hx, fabsf(Q.r.x), __fmaf_rn(cx, Q.r.x, Q.kf.x));
+  const float fy = __fmaf_rn(hy, fabsf(Q.r.y), __fmaf_rn(cy, Q.r.y, Q.kf.y));
+  const float fz = __fmaf_rn(hz, fabsf(Q.r.z), __fmaf_rn(cz, Q.r.z, Q.kf.z));
+  *lo = fmaxf(fmaxf(nx, ny), nz);
+  *hi = fminf(fminf(fx, fy), fz);
 }
 
 // ---- Möller–Trumbore, MathLib.cl:117-160 ---------------------------------------------------------------
@@ -207,14 +214,15 @@ RT_DEV bool validate_hit(const SceneView &S, v3 o, v3 d, int tri) {
 }
 
 // ---- reference-order traversal ---------------------------------------------------------------------------
+constexpr int kRefStack = 64;   // b200rt_set_scene routes trees that need more to REFERENCE mode with the caller's cap
+
 template <bool SMEM, bool STATS>
-RT_DEV Hit closest_hit_reference(const SceneView &S, v3 o, v3 d, TraceCounters *cnt) {
+RT_DEV Hit closest_hit_reference_cap(const SceneView &S, v3 o, v3 d, TraceCounters *cnt, const int cap) {
   Hit best;
   best.tri = -1;
   best.k = 1000.0f;
-  int stack[64];
+  int stack[kRefStack];
   int top = -1;
-  const int cap = S.stack_cap;
   stack[++top] = 0;
   while (top != -1) {
     int cur = stack[top--];
@@ -242,58 +250,18 @@ RT_DEV Hit closest_hit_reference(const SceneView &S, v3 o, v3 d, TraceCounters *
   return best;
 }
 
-// ---- exact front-to-back traversal (fallback; thread-local stack) ----------------------------------------------
-constexpr int kExactStack = 64;   // b200rt_set_scene routes deeper trees to the reference traversal
+template <bool SMEM, bool STATS>
+RT_DEV Hit closest_hit_reference(const SceneView &S, v3 o, v3 d, TraceCounters *cnt) {
+  return closest_hit_reference_cap<SMEM, STATS>(S, o, d, cnt, S.stack_cap);
+}
 
+// The reference's walk with a stack that cannot drop: what the fast path computes, obtained the slow way.  Out of
+// line: reached only by rays with a zero / denormal / huge direction component and by the (very rare) rays whose
+// fast-path winner fails validate_hit.
 template <bool SMEM>
-__device__ __noinline__ Hit closest_hit_exact(const SceneView &S, v3 o, v3 d) {
-  Hit best;
-  best.tri = -1;
-  best.k = 1000.0f;
-  int best_rank = 0x7fffffff;
-  float tmin, tmax;
-  if (!slab_exact(o, d, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4], S.root_box[5], &tmin,
-                  &tmax))
-    return best;
-  if (S.root_ref < 0) {
-    test_triangle<SMEM>(S, ~S.root_ref, o, d, best, best_rank);
-    return best;
-  }
-  float2 stack[kExactStack];
-  const float behind = -S.cull_abs;
-  int cur = 0, sp = 0;
-  for (;;) {
-    const float4 *p = S.nodes + cur;
-    float4 q0 = ld4<SMEM>(p), q1 = ld4<SMEM>(p + 1), q2 = ld4<SMEM>(p + 2), q3 = ld4<SMEM>(p + 3);
-    int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
-    float tminL, tmaxL, tminR, tmaxR;
-    bool goL = slab_exact(o, d, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tminL, &tmaxL);
-    bool goR = slab_exact(o, d, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tminR, &tmaxR);
-    float lim = best.k * 1.001f + S.cull_abs;
-    goL = goL && !(tminL > lim) && !(tmaxL < behind);
-    goR = goR && !(tminR > lim) && !(tmaxR < behind);
-    if (goL && refL < 0) { test_triangle<SMEM>(S, ~refL, o, d, best, best_rank); goL = false; }
-    if (goR && refR < 0) { test_triangle<SMEM>(S, ~refR, o, d, best, best_rank); goR = false; }
-    if (goL && goR) {
-      bool leftNear = tminL <= tminR;
-      stack[sp++] = make_float2(__int_as_float(leftNear ? refR : refL), leftNear ? tminR : tminL);
-      cur = leftNear ? refL : refR;
-    } else if (goL || goR) {
-      cur = goL ? refL : refR;
-    } else {
-      bool found = false;
-      while (sp > 0) {
-        float2 e = stack[--sp];
-        if (!(e.y > best.k * 1.001f + S.cull_abs)) {
-          cur = __float_as_int(e.x);
-          found = true;
-          break;
-        }
-      }
-      if (!found) break;
-    }
-  }
-  return best;
+__device__ __noinline__ Hit closest_hit_nodrop(const SceneView &S, v3 o, v3 d) {
+  TraceCounters dummy;
+  return closest_hit_reference_cap<SMEM, false>(S, o, d, &dummy, kRefStack);
 }
 
 // ---- fast traversal ---------------------------------------------------------------------------------------------
@@ -336,7 +304,7 @@ RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, int &pn, uint32_
   T.sp = 0;
   float lo, hi;
   if (STATS) cnt->box_tests++;
-  slab_cons(T.Q, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4], S.root_box[5], &lo, &hi);
+  slab_cons(T.Q, S.root_ch[0], S.root_ch[1], S.root_ch[2], S.root_ch[3], S.root_ch[4], S.root_ch[5], &lo, &hi);
   T.active = hi >= lo;
   if (T.active && S.root_ref < 0) {
     parks[0] = (uint32_t)S.root_ref;
@@ -401,7 +369,7 @@ RT_DEV void test_parked(const SceneView &S, Trav &T, uint32_t ref, v3 o, v3 d) {
 template <bool SMEM, bool STATS>
 RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, uint32_t *parks, int pstride,
                             TraceCounters *cnt) {
-  if (!ray_is_fast(S, o, d)) return closest_hit_exact<SMEM>(S, o, d);
+  if (!ray_is_fast(S, o, d)) return closest_hit_nodrop<SMEM>(S, o, d);
   Trav T;
   int pn = 0;
   trav_begin<SMEM, STATS>(S, T, o, d, pn, parks, cnt);
@@ -414,7 +382,7 @@ RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, uint32
       trav_step<SMEM, STATS>(S, T, pn, parks, pstride, st, cnt);
     }
   }
-  if (T.best.tri >= 0 && !validate_hit(S, o, d, T.best.tri)) return closest_hit_exact<SMEM>(S, o, d);
+  if (T.best.tri >= 0 && !validate_hit(S, o, d, T.best.tri)) return closest_hit_nodrop<SMEM>(S, o, d);
   return T.best;
 }
 

@@ -29,9 +29,16 @@ def main():
             st = ctx.stats()
             if best is None or st["total_ms"] < best["total_ms"]:
                 best = st
+        split = ""
+        try:
+            ctx.render(cam, env, w, h, spp, 4, opts=rt.make_opts(rng_mode=1, traversal=0, seed=0, time_kernels=True))
+            st = ctx.stats()
+            split = f" | k_trace {st['trace_kernel_ms']:.2f} k_shade {st['shade_kernel_ms']:.2f} ms"
+        except TypeError:
+            pass
         print(f"{os.path.basename(sys.argv[1])} {name} {w}x{h} spp{spp}: rays {best['rays']} total {best['total_ms']:.2f} ms "
               f"{best['rays'] / best['total_ms'] / 1e3:.1f} Mrays/s mean {float(out.mean()):.6f} primary {best['primary_ms']:.2f} ms "
-              f"launches {best['kernel_launches']} reval {best.get('revalidated')}", flush=True)
+              f"launches {best['kernel_launches']} reval {best.get('revalidated')}{split}", flush=True)
 
 
 if __name__ == "__main__":
