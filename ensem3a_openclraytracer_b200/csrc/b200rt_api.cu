@@ -55,7 +55,7 @@ struct b200rt_ctx {
   float cull_abs = 0.0f, cmax = 0.0f;
   int fast_ok = 1;
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
-  int quorum = 16, refill_min = 8, tri_quorum = 8;
+  int quorum = 20, refill_min = 8, tri_quorum = 4;
   std::vector<int32_t> tri_mat;  // for re-validating material edits
 
   // environment map
