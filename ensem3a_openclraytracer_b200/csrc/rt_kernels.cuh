@@ -641,6 +641,10 @@ __global__ void k_math_probe(int fn, const float *a, const float *b, long long n
     case 8: r = sqrtf(x); break;
     case 9: { float s, c; cr_sincos(x, &s, &c); r = s; break; }
     case 10: { float s, c; cr_sincos(x, &s, &c); r = c; break; }
+    case 11: r = (float)ibl_texel_u(x, y, 8192); break;                       // fast path with its fallback
+    case 12: r = (float)texel_coord(cr_atan2(x, y), 0.1591f, 8192); break;    // correctly rounded angle only
+    case 13: r = (float)ibl_texel_v(x, 4096); break;
+    case 14: r = (float)texel_coord(cr_asin(x), 0.3183f, 4096); break;
   }
   out[i] = r;
 }

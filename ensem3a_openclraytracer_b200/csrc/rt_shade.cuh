@@ -55,16 +55,39 @@ RT_DEV v3 camera_dir(const FrameParams &F, int i) {
   return d;
 }
 
+// uv * extent -> integer texel, exactly the reference's chain of binary32 roundings (MathLib.cl:78-80,87):
+// RN(RN(a * inv) + 0.5) * extent, truncated, clamped by the sampler.  Monotone non-decreasing in a.
+RT_DEV int texel_coord(float a, float inv, int extent) {
+  const float u = a * inv + 0.5f;
+  const int p = __float2int_rz(u * (float)extent);
+  return max(0, min(p, extent - 1));
+}
+
+// The environment lookup needs atan2 / asin only to pick a texel.  The binary32 library routines are within
+// 2 ulp of the true value, so the correctly rounded angle lies within 4 ulp of theirs; texel_coord is monotone,
+// so if both ends of that interval land in the same texel the texel is decided — otherwise (a lookup within
+// ~1e-6 of a texel boundary) the correctly rounded binary64 path is taken.
+RT_DEV int ibl_texel_u(float z, float x, int w) {
+  const float a = atan2f(z, x);
+  const float del = fabsf(a) * 4.76837158203125e-07f;  // 2^-21 >= 4 ulp
+  int p = texel_coord(a - del, 0.1591f, w);
+  if (p != texel_coord(a + del, 0.1591f, w)) p = texel_coord(cr_atan2(z, x), 0.1591f, w);
+  return p;
+}
+RT_DEV int ibl_texel_v(float y, int h) {
+  const float a = asinf(y);
+  const float del = fabsf(a) * 4.76837158203125e-07f;
+  int p = texel_coord(a - del, 0.3183f, h);
+  if (p != texel_coord(a + del, 0.3183f, h)) p = texel_coord(cr_asin(y), 0.3183f, h);
+  return p;
+}
+
 // MathLib.cl:72-90.  Integer texel coordinates through a clamp-to-edge sampler; UNORM8 -> b/255.
 RT_DEV v3 ibl_lookup(const FrameParams &F, cudaTextureObject_t tex, v3 dir) {
   dir = apply_rotor(F.ibl_r1, dir);
   dir = apply_rotor(F.ibl_r2, dir);
-  float u = cr_atan2(dir.z, dir.x) * 0.1591f + 0.5f;
-  float v = cr_asin(dir.y) * 0.3183f + 0.5f;
-  int px = __float2int_rz(u * (float)F.ibl_w);
-  int py = __float2int_rz(v * (float)F.ibl_h);
-  px = max(0, min(px, F.ibl_w - 1));
-  py = max(0, min(py, F.ibl_h - 1));
+  const int px = ibl_texel_u(dir.z, dir.x, F.ibl_w);
+  const int py = ibl_texel_v(dir.y, F.ibl_h);
   uchar4 t = tex2D<uchar4>(tex, (float)px + 0.5f, (float)py + 0.5f);
   return mk3(__fdiv_rn((float)t.x, 255.0f), __fdiv_rn((float)t.y, 255.0f), __fdiv_rn((float)t.z, 255.0f)) * 1.0f;
 }

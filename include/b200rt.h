@@ -154,7 +154,9 @@ int b200rt_img_processing(b200rt_ctx *ctx, const float *src, float *dst, int64_t
 int b200rt_get_stats(const b200rt_ctx *ctx, b200rt_stats *stats);
 
 /* Device math used by the kernels, exposed so tests can compare it value by value with the oracle:
- * fn 0 sin, 1 cos, 2 acos, 3 asin, 4 atan2(a,b), 5 tan, 6 pow(a,b), 7 a/b, 8 sqrt, 9/10 sincos. */
+ * fn 0 sin, 1 cos, 2 acos, 3 asin, 4 atan2(a,b), 5 tan, 6 pow(a,b), 7 a/b, 8 sqrt, 9/10 the samplers' sincos,
+ * 11/12 environment-map column of atan2(a,b) by the fast path / by the correctly rounded angle (8192 wide),
+ * 13/14 the same for the row of asin(a) (4096 high). */
 int b200rt_math_probe(b200rt_ctx *ctx, int fn, const float *a, const float *b, int64_t n, float *out);
 
 /* Philox4x32-10 block of the device implementation (known-answer tests). */

@@ -45,6 +45,24 @@ def test_transcendentals_are_correctly_rounded(gpu_ctx, fn, code, lo, hi):
     assert np.array_equal(bits(gpu_ctx.math_probe(code, a)), bits(oracle.math_probe(fn, a)))
 
 
+def test_environment_texel_fast_path_equals_exact_path(gpu_ctx):
+    """The environment lookup picks its texel from binary32 atan2f / asinf and falls back to the correctly rounded
+    angle only next to a texel boundary; both ways must select the same texel, everywhere."""
+    r = np.random.default_rng(7)
+    n = 1 << 22
+    z, x = r.standard_normal(n).astype(np.float32), r.standard_normal(n).astype(np.float32)
+    z[:6] = [0.0, -0.0, 1.0, -1.0, 0.0, 1e-30]
+    x[:6] = [1.0, -1.0, 0.0, 0.0, 0.0, -1.0]
+    assert np.array_equal(gpu_ctx.math_probe(11, z, x), gpu_ctx.math_probe(12, z, x))
+    y = r.uniform(-1, 1, n).astype(np.float32)
+    y[:6] = [0.0, -0.0, 1.0, -1.0, 1.0000001, 0.99999994]
+    assert np.array_equal(gpu_ctx.math_probe(13, y), gpu_ctx.math_probe(14, y))
+    # the exact path is the oracle's chain
+    a = oracle.math_probe("atan2", z, x)
+    want = np.clip(((a * np.float32(0.1591) + np.float32(0.5)) * np.float32(8192)).astype(np.int64), 0, 8191)
+    assert np.array_equal(gpu_ctx.math_probe(12, z, x).astype(np.int64), want)
+
+
 def test_atan2_pow_sqrt(gpu_ctx):
     r = np.random.default_rng(1)
     a, b = r.uniform(-1, 1, 1 << 20).astype(np.float32), r.uniform(-1, 1, 1 << 20).astype(np.float32)
