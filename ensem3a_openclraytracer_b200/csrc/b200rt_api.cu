@@ -744,7 +744,7 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   }
   c->cmax = cmax;
   // range the conservative slab test's error margin is proven for (rt_trace.cuh); outside it every ray takes
-  // closest_hit_exact
+  // closest_hit_nodrop
   c->fast_ok = (cmax <= 1.099511627776e12f /* 2^40 */ && cmax >= 9.5367431640625e-07f /* 2^-20 */) ? 1 : 0;
 
   // ---- upload -------------------------------------------------------------------------------------------------------------
