@@ -26,7 +26,8 @@ class Opts(ctypes.Structure):
     _fields_ = [("rng_mode", ctypes.c_int32), ("traversal", ctypes.c_int32), ("stack_cap", ctypes.c_int32),
                 ("output", ctypes.c_int32), ("sample_begin", ctypes.c_int32), ("sample_end", ctypes.c_int32),
                 ("pixel_begin", ctypes.c_int32), ("pixel_end", ctypes.c_int32), ("seed", ctypes.c_uint64),
-                ("collect_stats", ctypes.c_int32), ("time_kernels", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
+                ("collect_stats", ctypes.c_int32), ("time_kernels", ctypes.c_int32), ("tile_row_mod", ctypes.c_int32),
+                ("tile_row_rem", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2)]
 
 
 class Stats(ctypes.Structure):
@@ -122,13 +123,15 @@ def _i32(a):
 
 
 def make_opts(rng_mode=RNG_REFERENCE, traversal=TRAVERSAL_FAST, stack_cap=20, output=OUT_FINAL, sample_begin=0,
-              sample_end=0, pixel_begin=0, pixel_end=0, seed=0, collect_stats=False, time_kernels=False):
+              sample_end=0, pixel_begin=0, pixel_end=0, seed=0, collect_stats=False, time_kernels=False, tile_row_mod=0,
+              tile_row_rem=0):
     o = Opts()
     o.rng_mode, o.traversal, o.stack_cap, o.output = rng_mode, traversal, stack_cap, output
     o.sample_begin, o.sample_end, o.pixel_begin, o.pixel_end = sample_begin, sample_end, pixel_begin, pixel_end
     o.seed = seed & 0xFFFFFFFFFFFFFFFF
     o.collect_stats = 1 if collect_stats else 0
     o.time_kernels = 1 if time_kernels else 0
+    o.tile_row_mod, o.tile_row_rem = int(tile_row_mod), int(tile_row_rem)
     return o
 
 

@@ -171,6 +171,8 @@ void frame_setup(const b200rt_ctx *c, const float *cam, const float *env, int wi
   F->pixel_begin = o.pixel_begin;
   F->pixel_end = o.pixel_end;
   if (F->pixel_end <= 0) { F->pixel_begin = 0; F->pixel_end = width * height; }
+  F->tile_row_mod = o.tile_row_mod;
+  F->tile_row_rem = o.tile_row_rem;
   F->out_mode = o.output;
   F->rng_mode = o.rng_mode;
   F->key0 = (uint32_t)(o.seed & 0xffffffffull);
@@ -393,6 +395,8 @@ int check_frame_args(b200rt_ctx *c, const float *cam, int width, int height, int
     if ((o.sample_begin != 0 || o.sample_end != spp) && o.output != B200RT_OUT_SUMS)
       return fail(c, B200RT_ERR_INVALID, "a partial sample range only makes sense with B200RT_OUT_SUMS");
   }
+  if (o.tile_row_mod > 1 && (o.tile_row_rem < 0 || o.tile_row_rem >= o.tile_row_mod))
+    return fail(c, B200RT_ERR_INVALID, "bad tile row split %d mod %d", o.tile_row_rem, o.tile_row_mod);
   if (o.pixel_end > 0 && (o.pixel_begin < 0 || o.pixel_begin >= o.pixel_end || o.pixel_end > width * height))
     return fail(c, B200RT_ERR_INVALID, "bad pixel range [%d,%d)", o.pixel_begin, o.pixel_end);
   return 0;

@@ -118,6 +118,7 @@ RT_DEV int work_to_pixel(const KernelArgs &A, unsigned int w) {
   int tx = (int)(tile % (unsigned)A.tiles_x), ty = (int)(tile / (unsigned)A.tiles_x);
   int x = tx * 8 + (int)(in & 7u), y = ty * 4 + (int)(in >> 3);
   if (x >= A.F.width || y >= A.F.height) return -1;
+  if (A.F.tile_row_mod > 1 && ty % A.F.tile_row_mod != A.F.tile_row_rem) return -1;
   int i = y * A.F.width + x;
   if (i < A.F.pixel_begin || i >= A.F.pixel_end) return -1;
   return i;

@@ -22,6 +22,7 @@ struct FrameParams {
   int spp, max_bounce;
   int s0, s1;
   int pixel_begin, pixel_end;
+  int tile_row_mod, tile_row_rem;  // > 1: only tile rows with row % mod == rem (b200rt_opts)
   int out_mode;
   int rng_mode;
   uint32_t key0, key1;

@@ -12,8 +12,10 @@ order.  The per-rank float32 partial sums (width*height*3) are the only data tha
                    (peers finished writing / rank 0 finished reading).
 
 The reference's own generator is one serial stream per pixel (MathLib.cl:294-310) and cannot split
-a pixel's samples; with rng_mode=REFERENCE the frame is split by PIXEL ranges instead (disjoint
-pixels, so the reduce degenerates to a gather and is bit-exact).
+a pixel's samples; with rng_mode=REFERENCE the frame is split by PIXELS instead: rank r takes the rows of
+8x4-pixel tiles whose index is r modulo the number of ranks (interleaved, because the cost of a pixel varies by
+an order of magnitude between sky and geometry).  Disjoint pixels, so the reduce degenerates to a gather and is
+bit-exact.
 """
 import numpy as np
 
@@ -32,14 +34,12 @@ def split_range(n, parts):
 
 
 def rank_work(rank, world, width, height, spp, rng_mode):
-    """(sample_begin, sample_end, pixel_begin, pixel_end) of `rank`; an empty range has begin == end."""
+    """(sample_begin, sample_end, tile_row_mod, tile_row_rem) of `rank`; an empty sample range has begin == end,
+    tile_row_mod == 0 means every tile row."""
     if rng_mode == _capi.RNG_PHILOX:
         s0, s1 = split_range(spp, world)[rank]
-        return s0, s1, 0, width * height
-    # pixel split on whole rows of 8x4 tiles keeps every rank's work list tile-aligned
-    rows = (height + 3) // 4
-    r0, r1 = split_range(rows, world)[rank]
-    return 0, spp, min(r0 * 4, height) * width, min(r1 * 4, height) * width
+        return s0, s1, 0, 0
+    return 0, spp, (world if world > 1 else 0), (rank if world > 1 else 0)
 
 
 class _RawCudaBuffer:
@@ -116,17 +116,17 @@ class DistributedRenderer:
         torch, dist = self.torch, self.dist
         n = width * height * 3
         self._ensure(n)
-        s0, s1, p0, p1 = rank_work(self.rank, self.world, width, height, spp, rng_mode)
-        empty = (s0 == s1) or (p0 == p1)
+        s0, s1, tmod, trem = rank_work(self.rank, self.world, width, height, spp, rng_mode)
+        empty = (s0 == s1) or (tmod > 1 and trem >= (height + 3) // 4)
         if self.partial_fn is not None:
-            part = self.partial_fn(cam, env, width, height, spp, max_bounce, rng_mode, seed, s0, s1, p0, p1)
+            part = self.partial_fn(cam, env, width, height, spp, max_bounce, rng_mode, seed, s0, s1, tmod, trem)
             self._accum.copy_(torch.as_tensor(part, dtype=torch.float32))
         else:
             self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
             self._accum.zero_()
             if not empty:
                 opts = _capi.make_opts(rng_mode=rng_mode, traversal=traversal, output=_capi.OUT_SUMS, sample_begin=s0,
-                                       sample_end=s1, pixel_begin=p0, pixel_end=p1, seed=seed)
+                                       sample_end=s1, tile_row_mod=tmod, tile_row_rem=trem, seed=seed)
                 self.ctx.render_device(cam, env, width, height, spp, max_bounce, self._accum.data_ptr(), opts)
         if self.reduce == "peer":
             dist.all_reduce(self._flag, group=self.group)       # every rank's partial sums are complete

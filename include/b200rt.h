@@ -57,7 +57,9 @@ typedef struct {
   int32_t collect_stats; /* 1: also count box / triangle tests (slower) */
   int32_t time_kernels;  /* 1: bracket every k_shade / k_trace launch with CUDA events and report the sums
                             (stats.shade_kernel_ms / trace_kernel_ms); adds two event records per iteration */
-  int32_t reserved[4];
+  int32_t tile_row_mod;  /* > 1: of the frame's rows of 8x4-pixel tiles (4 pixel rows each) only those with        */
+  int32_t tile_row_rem;  /*   tile_row % tile_row_mod == tile_row_rem are rendered (interleaved multi-GPU split)  */
+  int32_t reserved[2];
 } b200rt_opts;
 
 typedef struct {

@@ -271,6 +271,27 @@ def test_sample_and_pixel_ranges(gpu_ctx):
     assert np.array_equal(bits(top + bot), bits(full))
 
 
+def test_interleaved_tile_rows_partition_the_frame(gpu_ctx):
+    """tile_row_mod / tile_row_rem (the multi-GPU split of the reference-RNG mode): N interleaved partial renders
+    touch disjoint pixels and add up, bit for bit, to the full frame."""
+    sc = fixtures.load_scene("serre")
+    fixtures.upload(gpu_ctx, sc)
+    W, H, spp = 72, 50, 3                       # 13 tile rows, the last one partial
+    cam, env = fixtures.cam_env(sc["params"], W, H)
+    full = gpu_ctx.render(cam, env, W, H, spp, 4, opts=rt.make_opts(output=rt.OUT_SUMS))
+    acc = np.zeros_like(full)
+    for rem in range(3):
+        part = gpu_ctx.render(cam, env, W, H, spp, 4, opts=rt.make_opts(output=rt.OUT_SUMS, tile_row_mod=3, tile_row_rem=rem))
+        rows = part.reshape(H, W, 3)
+        for y in range(H):
+            if (y // 4) % 3 != rem:
+                assert not rows[y].any()
+        acc += part
+    assert np.array_equal(bits(acc), bits(full))
+    with pytest.raises(rt.B200RTError):
+        gpu_ctx.render(cam, env, W, H, spp, 4, opts=rt.make_opts(tile_row_mod=3, tile_row_rem=3))
+
+
 def test_edge_cases(gpu_ctx):
     sc = fixtures.load_scene("cornell")
     ibl = fixtures.load_ibl()

@@ -32,10 +32,10 @@ def test_split_range_covers_everything():
 def test_rank_work_partitions():
     W, H, spp = 50, 30, 10
     s = [multigpu.rank_work(r, 4, W, H, spp, _capi.RNG_PHILOX) for r in range(4)]
-    assert [x[:2] for x in s] == [(0, 3), (3, 6), (6, 8), (8, 10)] and all(x[2:] == (0, W * H) for x in s)
+    assert [x[:2] for x in s] == [(0, 3), (3, 6), (6, 8), (8, 10)] and all(x[2:] == (0, 0) for x in s)
     p = [multigpu.rank_work(r, 4, W, H, spp, _capi.RNG_REFERENCE) for r in range(4)]
-    assert p[0][2] == 0 and p[-1][3] == W * H and all(a[3] == b[2] for a, b in zip(p, p[1:]))
-    assert all(x[:2] == (0, spp) for x in p) and all(x[2] % (4 * W) == 0 for x in p)
+    assert all(x[:2] == (0, spp) for x in p) and [x[2:] for x in p] == [(4, 0), (4, 1), (4, 2), (4, 3)]
+    assert multigpu.rank_work(0, 1, W, H, spp, _capi.RNG_REFERENCE) == (0, spp, 0, 0)
 
 
 def reference_finalize(sums, spp):
@@ -61,11 +61,16 @@ def _worker(rank, world, port, rng_mode, q):
     W, H, spp, mb = 40, 24, 6, 3
     cam, env = fixtures.cam_env(sc["params"], W, H)
 
-    def partial_fn(cam, env, width, height, spp, max_bounce, rng, seed, s0, s1, p0, p1):
-        if s0 == s1 or p0 == p1:
-            return np.zeros(width * height * 3, np.float32)
-        out, _ = oracle.render(sc, cam, env, width * height, spp, max_bounce, ibl, i0=p0, i1=p1, rng_mode=rng,
-                               seed=seed, s0=s0, s1=s1, raw_sums=True, nthreads=2)
+    def partial_fn(cam, env, width, height, spp, max_bounce, rng, seed, s0, s1, tmod, trem):
+        out = np.zeros(width * height * 3, np.float32)
+        if s0 == s1:
+            return out
+        tile_rows = range((height + 3) // 4)
+        for ty in (tile_rows if tmod <= 1 else [t for t in tile_rows if t % tmod == trem]):
+            i0, i1 = ty * 4 * width, min((ty + 1) * 4, height) * width      # one row of 8x4-pixel tiles
+            part, _ = oracle.render(sc, cam, env, width * height, spp, max_bounce, ibl, i0=i0, i1=i1, rng_mode=rng,
+                                    seed=seed, s0=s0, s1=s1, raw_sums=True, nthreads=2)
+            out[3 * i0:3 * i1] = part[3 * i0:3 * i1]
         return out
 
     dr = multigpu.DistributedRenderer(None, rank, world, reduce="nccl", partial_fn=partial_fn,
