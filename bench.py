@@ -60,6 +60,24 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def cpu_renderer():
+    """(kind, render(sc, cam, env, img_dim, spp, max_bounce, ibl, i0, i1) -> (image, rays)) of the CPU arm:
+    oracle/_ref (the reference's own kernel text compiled by g++) when it is present, else the C restatement of
+    oracle/ (bit-identical to it, tests/test_oracle_vs_ref.py).  The only place bench.py executes oracle/."""
+    from oracle import ref_lib
+    if ref_lib.available() and ref_lib.available("libclref_count.so"):
+        def render(sc, cam, env, img_dim, spp, mb, ibl, i0, i1, count=False):
+            out, cnt = ref_lib.raytrace(sc, cam, env, img_dim, spp, mb, ibl, i0=i0, i1=i1, counters=count)
+            return out, (cnt["rays"] if cnt else None)
+        return "reference", render
+    from oracle import oracle
+
+    def render(sc, cam, env, img_dim, spp, mb, ibl, i0, i1, count=False):
+        out, cnt = oracle.render(sc, cam, env, img_dim, spp, mb, ibl, i0=i0, i1=i1)
+        return out, cnt["rays"]
+    return "port", render
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -116,26 +134,21 @@ def run_reference_arm(args, rank):
     host core, on a bounded sample of the workload per step.  Executes oracle/ — allowed only here."""
     if rank != 0:
         return
-    from oracle import ref_lib
+    kind, render = cpu_renderer()
     sc, ibl, cam, env = load_workload()
     W, H = WORKLOAD["width"], WORKLOAD["height"]
-    if not ref_lib.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libclref.so is missing (build() makes it where "
-                          "/root/reference exists)"}))
-        return
     cores = os.cpu_count() or 1
     spp = 16
     rows = max(8, min(H, 6 * cores))           # a band of rows through the middle of the frame
     i0 = (H // 2 - rows // 2) * W
     i1 = i0 + rows * W
     sample = f"{rows} rows x {W} px x {spp} spp of the workload frame (reference RNG), {cores} OpenMP threads"
-    # ray count of the sample from the counting build (untimed; the kernel is deterministic)
-    _, cnt = ref_lib.raytrace(sc, cam, env, W * H, spp, WORKLOAD["max_bounce"], ibl, i0=i0, i1=i1, counters=True)
-    rays = cnt["rays"]
+    # ray count of the sample (untimed counting run; the kernel is deterministic)
+    _, rays = render(sc, cam, env, W * H, spp, WORKLOAD["max_bounce"], ibl, i0, i1, count=True)
     times = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        ref_lib.raytrace(sc, cam, env, W * H, spp, WORKLOAD["max_bounce"], ibl, i0=i0, i1=i1)
+        render(sc, cam, env, W * H, spp, WORKLOAD["max_bounce"], ibl, i0, i1)
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             times.append(dt)
@@ -146,7 +159,7 @@ def run_reference_arm(args, rank):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "sample": sample},
             "samples_per_s": (i1 - i0) * spp * len(times) / total,
-            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -154,10 +167,8 @@ def run_reference_arm(args, rank):
 
 def cpu_baseline_leg(ctx, sc, ibl, cam, env):
     """Bounded CPU run of oracle/_ref beside the GPU number + parity of the same pixels."""
-    from oracle import ref_lib
     import ensem3a_openclraytracer_b200 as rt
-    if not ref_lib.available():
-        return None, None
+    kind, render = cpu_renderer()
     W, H = WORKLOAD["width"], WORKLOAD["height"]
     cores = os.cpu_count() or 1
     spp = 64
@@ -165,7 +176,7 @@ def cpu_baseline_leg(ctx, sc, ibl, cam, env):
     i0 = (H // 2 - rows // 2) * W
     i1 = i0 + rows * W
     t0 = time.perf_counter()
-    ref, _ = ref_lib.raytrace(sc, cam, env, W * H, spp, WORKLOAD["max_bounce"], ibl, i0=i0, i1=i1)
+    ref, _ = render(sc, cam, env, W * H, spp, WORKLOAD["max_bounce"], ibl, i0, i1)
     dt = time.perf_counter() - t0
     # same pixels, same (reference) generator on the GPU: ray count + parity
     o = rt.make_opts(rng_mode=rt.RNG_REFERENCE, pixel_begin=i0, pixel_end=i1)
@@ -175,7 +186,7 @@ def cpu_baseline_leg(ctx, sc, ibl, cam, env):
     rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
     parity = {"pixels": i1 - i0, "spp": spp, "identical_frac": float(np.mean(a == b)), "max_rel": float(rel.max()),
               "rmse": float(np.sqrt(np.mean((a - b) ** 2)))}
-    base = {"value": st["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+    base = {"value": st["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
             "sample": f"{rows} rows x {W} px x {spp} spp of the workload frame (reference RNG), {dt:.1f} s on {cores} "
                       f"OpenMP threads; samples/s {(i1 - i0) * spp / dt:.0f}"}
     return base, parity
