@@ -341,11 +341,15 @@ def main():
     n_trace = (launches_step - 1) // 2                      # k_primary + (n_iter + 1) k_shade + n_iter k_trace
     trace_rays = stp["rays"] - W * H                        # rank 0's rays minus the primary rays of k_primary
     achieved = trace_rays * bytes_per_ray / (stp["trace_kernel_ms"] * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_view = None, None
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("k_trace_dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            traffic = pj.get("k_trace_dram_bytes_per_launch")
+            ncu_view = {k: pj[k] for k in ("k_trace_ipc_of_4", "k_trace_active_threads_per_instruction_of_32",
+                                           "k_trace_l1tex_throughput_pct", "k_trace_alu_pipe_pct", "k_trace_fma_pipe_pct",
+                                           "k_trace_l1_hit_pct", "binding_unit") if k in pj}
         except Exception:
             traffic = None
     line = {
@@ -371,7 +375,10 @@ def main():
                      "kernel_ms_per_step": stp["trace_kernel_ms"], "k_shade_ms_per_step": stp["shade_kernel_ms"],
                      "k_primary_ms_per_step": stp["primary_ms"], "step_ms_profiled": stp["total_ms"],
                      "share_of_step": stp["trace_kernel_ms"] / stp["total_ms"],
-                     "note": "algorithmic bytes in the reference's layout; the 2 MB scene is cache-resident"},
+                     "note": "algorithmic bytes in the reference's layout and visiting order (SURVEY 8d); the 2 MB scene is "
+                             "cache-resident, so this is a traffic-equivalent and frac may exceed 1; `ncu` holds the "
+                             "committed profile of the same kernel (profiles/), which names the unit that binds",
+                     "ncu": ncu_view},
     }
     if world == 1 and not args.no_cpu_baseline:
         ctx.set_stream(None)
