@@ -29,12 +29,31 @@ def load_scene(name):
 
 
 def load_ibl(name="preview"):
+    """preview (the 600x300 map of the reference checkout) | grey (uniform) | 8k (8192x4096 stand-in)"""
     if name == "grey":
         return np.full((8, 16, 4), 128, np.uint8)
+    if name == "8k":
+        if "ibl_8k" not in _cache:
+            _cache["ibl_8k"] = _ibl_8k()
+        return _cache["ibl_8k"]
     key = "ibl_" + name
     if key not in _cache:
         _cache[key] = np.ascontiguousarray(np.load(os.path.join(GOLDEN, "ibl_preview.npz"))["rgba"])
     return _cache[key]
+
+
+def _ibl_8k():
+    """8192x4096 stand-in for the missing IBL/Arches_E_PineTree_8k.jpg: bilinear upscale of the 600x300 preview."""
+    src = load_ibl("preview").astype(np.float32)
+    h, w = src.shape[:2]
+    H, W = 4096, 8192
+    y = (np.arange(H) + 0.5) * h / H - 0.5
+    x = (np.arange(W) + 0.5) * w / W - 0.5
+    y0 = np.clip(np.floor(y).astype(int), 0, h - 1); y1 = np.clip(y0 + 1, 0, h - 1); fy = np.clip(y - y0, 0, 1)[:, None, None]
+    x0 = np.clip(np.floor(x).astype(int), 0, w - 1); x1 = np.clip(x0 + 1, 0, w - 1); fx = np.clip(x - x0, 0, 1)[None, :, None]
+    top = src[y0][:, x0] * (1 - fx) + src[y0][:, x1] * fx
+    bot = src[y1][:, x0] * (1 - fx) + src[y1][:, x1] * fx
+    return np.ascontiguousarray(np.clip(np.rint(top * (1 - fy) + bot * fy), 0, 255).astype(np.uint8))
 
 
 def golden():

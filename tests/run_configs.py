@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
-"""BASELINE.json configs 1-4 at their named sizes on one GPU (config 5: tools/config5_run.py; config 2 is also
-bench.py's workload).  One JSON line per config: device time, Mrays/s, Msamples/s, kernel split, and a bounded
+"""TEST-SIDE MEASUREMENT SCRIPT (it executes oracle/_ref as the CPU arm and parity checker, which only code
+under tests/ and bench.py may do).  BASELINE.json configs 1-4 at their named sizes on one GPU (config 5:
+tools/config5_run.py; config 2 is also bench.py's workload).  One JSON line per config: device time, Mrays/s, Msamples/s, kernel split, and a bounded
 CPU run of the reference's own kernels (oracle/_ref, all host threads) on a band of the same frame with parity.
-usage: configs_run.py [spp_scale=1.0]   (spp_scale < 1 shortens configs 3 and 4)"""
+usage: python tests/run_configs.py [spp_scale=1.0]   (spp_scale < 1 shortens configs 3 and 4)"""
 import json
 import os
 import sys
@@ -15,20 +16,6 @@ sys.path.insert(0, ROOT)
 import ensem3a_openclraytracer_b200 as rt  # noqa: E402
 from oracle import ref_lib  # noqa: E402   (checker / CPU baseline only)
 from tests import fixtures  # noqa: E402
-
-
-def ibl_8k():
-    """8192x4096 stand-in for the missing IBL/Arches_E_PineTree_8k.jpg: bilinear upscale of the 600x300 preview."""
-    src = fixtures.load_ibl("preview").astype(np.float32)
-    h, w = src.shape[:2]
-    H, W = 4096, 8192
-    y = (np.arange(H) + 0.5) * h / H - 0.5
-    x = (np.arange(W) + 0.5) * w / W - 0.5
-    y0 = np.clip(np.floor(y).astype(int), 0, h - 1); y1 = np.clip(y0 + 1, 0, h - 1); fy = np.clip(y - y0, 0, 1)[:, None, None]
-    x0 = np.clip(np.floor(x).astype(int), 0, w - 1); x1 = np.clip(x0 + 1, 0, w - 1); fx = np.clip(x - x0, 0, 1)[None, :, None]
-    top = src[y0][:, x0] * (1 - fx) + src[y0][:, x1] * fx
-    bot = src[y1][:, x0] * (1 - fx) + src[y1][:, x1] * fx
-    return np.ascontiguousarray(np.clip(np.rint(top * (1 - fy) + bot * fy), 0, 255).astype(np.uint8))
 
 
 CONFIGS = [
@@ -47,7 +34,7 @@ def main():
     cores = os.cpu_count() or 1
     for c in CONFIGS:
         sc = fixtures.load_scene(c["scene"])
-        ibl = ibl_8k() if c["ibl"] == "8k" else fixtures.load_ibl(c["ibl"])
+        ibl = fixtures.load_ibl(c["ibl"])
         fixtures.upload(ctx, sc, ibl)
         W, H = c["w"], c["h"]
         spp = max(4, int(round(c["spp"] * scale))) if c.get("scale") else c["spp"]

@@ -81,6 +81,15 @@ def test_missing_library_is_an_error(monkeypatch):
         _capi.load_library()
 
 
+def test_tools_do_not_import_the_oracle():
+    """Development tools under tools/ drive the product only; anything that needs the checker lives in tests/."""
+    tdir = os.path.join(ROOT, "tools")
+    for f in sorted(os.listdir(tdir)):
+        if f.endswith(".py"):
+            text = open(os.path.join(tdir, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"tools/{f} imports oracle"
+
+
 def test_product_does_not_import_the_oracle():
     """Nothing under the package may reference oracle/ (the checker is never the product)."""
     pkg = os.path.join(ROOT, "ensem3a_openclraytracer_b200")

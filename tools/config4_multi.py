@@ -16,7 +16,6 @@ import torch.distributed as dist  # noqa: E402
 import ensem3a_openclraytracer_b200 as rt  # noqa: E402
 from ensem3a_openclraytracer_b200.multigpu import DistributedRenderer  # noqa: E402
 from tests import fixtures  # noqa: E402
-from tools.configs_run import ibl_8k  # noqa: E402
 
 
 def main():
@@ -25,7 +24,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sc = fixtures.load_scene("serre")
-    ibl = ibl_8k()
+    ibl = fixtures.load_ibl("8k")
     W, H = 3840, 2160
     cam, env = fixtures.cam_env(sc["params"], W, H)
     ctx = rt.Context(local)
