@@ -9,7 +9,8 @@ from ._capi import (B200RTError, Context, Opts, Stats, make_opts, build_library,
                     OUT_FINAL, OUT_SUMS)
 from .KernelLauncher import KernelLauncher
 from .BVH import BVH
+from .progressive import ProgressiveRender
 
 __all__ = ["B200RTError", "Context", "Opts", "Stats", "make_opts", "build_library", "load_library", "LIB_PATH",
-           "KernelLauncher", "BVH", "build_bvh", "RNG_REFERENCE", "RNG_PHILOX", "TRAVERSAL_FAST", "TRAVERSAL_REFERENCE",
+           "KernelLauncher", "BVH", "ProgressiveRender", "build_bvh", "RNG_REFERENCE", "RNG_PHILOX", "TRAVERSAL_FAST", "TRAVERSAL_REFERENCE",
            "TRAVERSAL_VERIFY", "OUT_FINAL", "OUT_SUMS"]

@@ -250,3 +250,28 @@ def test_rgb8_output_matches_saveimg_conversion(gpu_ctx):
     assert u.shape == (64, 96, 3) and u.dtype == np.uint8
     assert np.array_equal(u, (f.reshape(64, 96, 3) * 255).astype("uint8"))
     assert u.max() > 0
+
+
+def test_progressive_accumulation_and_resume(gpu_ctx):
+    """Slices of the sample range add up to the one-shot frame (float summation order aside), every step yields a
+    preview, and a saved (sums, done) state resumes to the same result."""
+    sc = fixtures.load_scene("cornell")
+    fixtures.upload(gpu_ctx, sc)
+    W, H, spp = 64, 48, 10
+    cam, env = fixtures.cam_env(sc["params"], W, H)
+    full = gpu_ctx.render(cam, env, W, H, spp, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=4))
+    pr = rt.ProgressiveRender(gpu_ctx, cam, env, W, H, spp, 4, slice_spp=4, seed=4)
+    previews = list(pr)
+    assert len(previews) == 3 and pr.done == spp
+    np.testing.assert_allclose(previews[-1], full, rtol=1e-5, atol=1e-6)
+    # the first preview is the 4-sample estimate
+    four = gpu_ctx.render(cam, env, W, H, spp, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=4, output=rt.OUT_SUMS,
+                                                                    sample_begin=0, sample_end=4))
+    assert np.array_equal(bits(previews[0]), bits(rt.progressive.finalize(four, 4)))
+    # checkpoint after the first slice, resume in a new object
+    a = rt.ProgressiveRender(gpu_ctx, cam, env, W, H, spp, 4, slice_spp=4, seed=4)
+    next(a)
+    b = rt.ProgressiveRender(gpu_ctx, cam, env, W, H, spp, 4, slice_spp=4, seed=4, sums=a.sums, done=a.done)
+    for _ in b:
+        pass
+    assert np.array_equal(bits(b.image()), bits(previews[-1]))
