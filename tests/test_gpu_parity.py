@@ -311,6 +311,27 @@ def test_edge_cases(gpu_ctx):
     assert np.array_equal(bits(gpu_ctx.render(cam, env, 40, 40, 3, 4)), bits(want))
 
 
+def test_one_triangle_scene(gpu_ctx):
+    """A tree that is a single leaf (no interior node at all): root box, root triangle, nothing else."""
+    sc = fixtures.load_scene("cornell")
+    face = sc["faceData"].reshape(-1, 10)[4:5].copy().reshape(-1)         # one wall triangle
+    one = dict(sc, faceData=face, lightData=np.zeros(0, np.int32))
+    one["BVH"] = rt.build_bvh(face, sc["V_p"])
+    assert one["BVH"].size == 9
+    ibl = fixtures.load_ibl()
+    fixtures.upload(gpu_ctx, one, ibl)
+    cam, env = fixtures.cam_env(sc["params"], 48)
+    env[4] = 1.0
+    for trav in TRAVERSALS:
+        want, cnt = oracle.render(one, cam, env, 48 * 48, 3, 4, ibl)
+        out = gpu_ctx.render(cam, env, 48, 48, 3, 4, opts=rt.make_opts(traversal=trav))
+        assert np.array_equal(bits(out), bits(want)), trav
+        assert gpu_ctx.stats()["rays"] == cnt["rays"]
+    tri, k = gpu_ctx.primary_hits(cam, 48, 48)
+    prim = oracle.primary(one, cam, 48 * 48)
+    assert np.array_equal(tri, prim["tri"]) and np.array_equal(bits(k), bits(prim["k"])) and (tri >= 0).any()
+
+
 def test_nan_and_inf_semantics_survive(gpu_ctx):
     """inf * 0 -> NaN -> fmax(fmin(NaN,1),0) = 1 (white pixel) must come out as in the reference."""
     sc = fixtures.load_scene("cornell")
