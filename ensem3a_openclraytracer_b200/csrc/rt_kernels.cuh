@@ -21,7 +21,7 @@ namespace b200rt {
 
 constexpr int kBlock = 128;        // k_primary, k_trace, k_trace_rays
 constexpr int kShadeBlock = 128;
-constexpr unsigned kChunk = 64;    // rays a warp claims from the list per atomic
+constexpr unsigned kChunk = 32;    // rays a warp claims from the list per atomic
 
 struct DeviceCounters {
   unsigned long long rays, box_tests, tri_tests, mismatches, samples, revalidated;
