@@ -183,8 +183,12 @@ size_t scene_smem_bytes(const b200rt_ctx *c) { return (size_t)c->n_inner * 80 + 
 
 bool use_smem_scene(const b200rt_ctx *c) { return scene_smem_bytes(c) <= kSmemSceneMax; }
 
+// entries of the per-lane shared-memory traversal stack: the near-first walk holds at most one entry per level;
+// trees walked in reference order keep their stack in thread-local memory instead
+int stack_entries(const b200rt_ctx *c) { return c->canonical ? c->depth + 2 : 2; }
+
 size_t smem_bytes(const b200rt_ctx *c, bool smem_scene) {
-  return lane_smem_bytes(c->depth + 2) + (smem_scene ? scene_smem_bytes(c) : 0);
+  return lane_smem_bytes(stack_entries(c)) + (smem_scene ? scene_smem_bytes(c) : 0);
 }
 
 void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float *d_out, KernelArgs *A) {
@@ -220,7 +224,7 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   A->counters = c->d_counters;
   A->n_nodes = c->n_inner;
   A->n_tris = c->n_tris;
-  A->stack_depth = c->depth + 2;
+  A->stack_depth = stack_entries(c);
   A->tiles_x = (F.width + 7) / 8;
   int tiles_y = (F.height + 3) / 4;
   A->n_work = A->tiles_x * tiles_y * 32;
@@ -693,6 +697,8 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   }
   if (!(cmax < INFINITY)) return fail(c, B200RT_ERR_INVALID, "scene contains a non-finite coordinate");
   if (c->ref_stack_need > kRefStack) canonical = false;  // closest_hit_nodrop's thread-local stack
+  // a pathologically deep tree would not leave room for the per-lane stacks in shared memory
+  if (lane_smem_bytes(c->depth + 2) > 96 * 1024) canonical = false;
 
   // ---- repack interior nodes breadth-first into the 64-byte two-child layout --------------------------------------
   std::vector<float4> nodes;
