@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
-"""BASELINE config 4 on N GPUs (torchrun): Serre_leger, 3840x2160, 8192x4096 environment map, the frame split
-across ranks — by tile rows with the reference generator (bit-exact against one GPU) and by sample ranges with
-Philox.  Rank 0 prints one JSON line per mode.
-usage: torchrun --nproc-per-node N tools/config4_multi.py [spp=64]"""
+"""One fixture scene on N GPUs (torchrun), the frame split across ranks — by tile rows with the reference generator
+(bit-exact against one GPU) and by sample ranges with Philox — timed against the same frame on one GPU.
+Rank 0 prints one JSON line per mode.  Defaults = BASELINE config 4 (Serre_leger, 3840x2160, 8k map).
+usage: torchrun --nproc-per-node N tools/multi_run.py [spp=64] [scene=serre] [width=3840] [height=2160] [ibl=8k]"""
 import json
 import os
 import sys
@@ -20,12 +20,15 @@ from tests import fixtures  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    spp = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    a = sys.argv[1:]
+    spp = int(a[0]) if len(a) > 0 else 64
+    scene = a[1] if len(a) > 1 else "serre"
+    W, H = (int(a[2]), int(a[3])) if len(a) > 3 else (3840, 2160)
+    ibl_name = a[4] if len(a) > 4 else "8k"
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    sc = fixtures.load_scene("serre")
-    ibl = fixtures.load_ibl("8k")
-    W, H = 3840, 2160
+    sc = fixtures.load_scene(scene)
+    ibl = fixtures.load_ibl(ibl_name)
     cam, env = fixtures.cam_env(sc["params"], W, H)
     ctx = rt.Context(local)
     fixtures.upload(ctx, sc, ibl)
@@ -54,7 +57,7 @@ def main():
             st = ctx.stats()
             ctx.set_stream(stream.cuda_stream)
             rel = np.abs(multi - single) / np.maximum(np.abs(single), 1e-3)
-            line = dict(config=4, split=name, n_gpus=world, width=W, height=H, spp=spp, ms=float(t.item()),
+            line = dict(scene=scene, split=name, n_gpus=world, width=W, height=H, spp=spp, ms=float(t.item()),
                         single_gpu_ms=st["total_ms"], speedup=st["total_ms"] / float(t.item()),
                         mrays_s=st["rays"] / float(t.item()) / 1e3, identical_frac=float(np.mean(multi == single)),
                         max_rel=float(rel.max()), rmse=float(np.sqrt(np.mean((multi - single) ** 2))))
