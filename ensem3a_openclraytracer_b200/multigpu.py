@@ -17,8 +17,6 @@ a pixel's samples; with rng_mode=REFERENCE the frame is split by PIXELS instead:
 an order of magnitude between sky and geometry).  Disjoint pixels, so the reduce degenerates to a gather and is
 bit-exact.
 """
-import numpy as np
-
 from . import _capi
 
 
