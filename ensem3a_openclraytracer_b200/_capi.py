@@ -36,10 +36,11 @@ class Stats(ctypes.Structure):
                 ("trace_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("upload_ms", ctypes.c_float),
                 ("kernel_launches", ctypes.c_int32), ("nodes", ctypes.c_int32), ("triangles", ctypes.c_int32),
                 ("bvh_depth", ctypes.c_int32), ("scene_in_smem", ctypes.c_int32), ("revalidated", ctypes.c_int32),
-                ("shade_kernel_ms", ctypes.c_float), ("trace_kernel_ms", ctypes.c_float)]
+                ("shade_kernel_ms", ctypes.c_float), ("trace_kernel_ms", ctypes.c_float), ("repack_ms", ctypes.c_float),
+                ("ref_stack_need", ctypes.c_int32), ("exact_walks", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
 # every symbol include/b200rt.h declares (tests/test_abi.py checks the header against this list)
@@ -49,7 +50,7 @@ SYMBOLS = [
     "b200rt_reduce_finalize_device", "b200rt_sync", "b200rt_set_stream", "b200rt_invalidate", "b200rt_primary_hits", "b200rt_trace_rays",
     "b200rt_img_processing", "b200rt_get_stats", "b200rt_math_probe", "b200rt_philox_probe", "b200rt_alloc",
     "b200rt_free", "b200rt_ipc_export",
-    "b200rt_ipc_open", "b200rt_ipc_close", "b200rt_build_bvh", "b200rt_version",
+    "b200rt_ipc_open", "b200rt_ipc_close", "b200rt_build_bvh", "b200rt_repack_probe", "b200rt_version",
 ]
 
 _lib = None
@@ -102,6 +103,8 @@ def load_library():
     lib.b200rt_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
     lib.b200rt_ipc_close.argtypes = [vp, vp]
     lib.b200rt_build_bvh.argtypes = [vp, i64, vp, i64, vp, i64, ctypes.POINTER(ctypes.c_int32)]
+    if "b200rt_repack_probe" in SYMBOLS:
+        lib.b200rt_repack_probe.argtypes = [vp, i64, vp, i64, vp, i64, i64, vp, i64, vp, i64, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("b200rt_version", "b200rt_last_error", "b200rt_default_opts", "b200rt_destroy"):
@@ -148,6 +151,27 @@ def build_bvh(face_data, vertex_p, return_depth=False):
         raise B200RTError(f"b200rt_build_bvh failed ({rc}): malformed buffers, more than 2^23 triangles, or a node whose "
                           "centroids all fall on one side of their mean (BVH.py does not terminate on such input)")
     return (out, depth.value) if return_depth else out
+
+
+def repack_probe(vertex_p, vertex_n, face_data, n_materials, bvh):
+    """(nodes[n_inner, 8] uint32, info dict) — the interior-node records b200rt_set_scene would upload (host only)."""
+    lib = load_library()
+    vp_, vn_, face, bvh_ = _f32(vertex_p), _f32(vertex_n), _i32(face_data), _f32(bvh)
+    info = np.zeros(20, np.float32)
+    rc = lib.b200rt_repack_probe(_ptr(vp_), vp_.size, _ptr(vn_), vn_.size, _ptr(face), face.size, int(n_materials),
+                                 _ptr(bvh_), bvh_.size, None, 0, _ptr(info))
+    if rc != 0:
+        raise B200RTError(f"b200rt_repack_probe failed ({rc})")
+    nodes = np.zeros((int(info[0]), 8), np.uint32)
+    rc = lib.b200rt_repack_probe(_ptr(vp_), vp_.size, _ptr(vn_), vn_.size, _ptr(face), face.size, int(n_materials),
+                                 _ptr(bvh_), bvh_.size, _ptr(nodes), nodes.size, _ptr(info))
+    if rc != 0:
+        raise B200RTError(f"b200rt_repack_probe failed ({rc})")
+    d = dict(n_inner=int(info[0]), node_f4=int(info[1]), depth=int(info[2]), ref_stack_need=int(info[3]),
+             canonical=bool(info[4]), fast_ok=bool(info[5]), cmax=float(info[6]), cull_abs=float(info[7]),
+             grid_base=info[8:11].copy(), grid_pitch=info[11:14].copy(), root_fc=info[14:17].copy(),
+             root_hq=info[17:20].copy())
+    return nodes, d
 
 
 class Context:

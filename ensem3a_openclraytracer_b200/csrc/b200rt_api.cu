@@ -15,14 +15,13 @@
 
 #include "../../include/b200rt.h"
 #include "rt_kernels.cuh"
+#include "scene_repack.h"
 
 using namespace b200rt;
 
 namespace {
 
 thread_local std::string g_create_error;
-
-constexpr size_t kSmemSceneMax = 48 * 1024;  // repacked nodes + triangles up to this size are staged in shared memory
 
 struct DevBuf {
   void *p = nullptr;
@@ -46,16 +45,18 @@ struct b200rt_ctx {
   bool have_scene = false;
   bool have_scene_cached = false;  // scene_hash / ibl_hash are valid
   uint64_t scene_hash = 0, mat_hash = 0;
-  DevBuf d_nodes, d_tris, d_normals, d_tboxes, d_frames, d_mats, d_bvh9;
+  DevBuf d_nodes, d_tris, d_normals, d_tboxes, d_frames, d_mats, d_bvh9, d_leafcnt;
   int n_nodes9 = 0, n_inner = 0, n_tris = 0, n_mats = 0;
   int depth = 0, ref_stack_need = 0;
   bool canonical = true;
   int root_ref = 0;
-  float root_ch[6] = {0, 0, 0, 0, 0, 0};
+  int node_f4 = 2;
+  float grid_base[3] = {0, 0, 0}, grid_pitch[3] = {1, 1, 1}, root_fc[3] = {0.5f, 0.5f, 0.5f}, root_hq[3] = {0, 0, 0};
   float cull_abs = 0.0f, cmax = 0.0f;
   int fast_ok = 1;
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
   int quorum = 20, refill_min = 8, tri_quorum = 4;
+  int max_trace_ctas = 0;  // B200RT_MAX_TRACE_CTAS: cap on resident k_trace CTAs per SM (0 = what fits)
   std::vector<int32_t> tri_mat;  // for re-validating material edits
 
   // environment map
@@ -92,6 +93,13 @@ int fail(b200rt_ctx *c, int code, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(c, B200RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
+}  // namespace
+
+static_assert(kRefStack == kRefStackMax, "scene_repack.h and rt_trace.cuh disagree on the exact walk's stack");
+size_t b200rt::lane_smem_bytes_host(int stack_depth) { return lane_smem_bytes(stack_depth); }
+
+namespace {
+
 int ensure(b200rt_ctx *c, DevBuf &b, size_t bytes) {
   if (bytes == 0) bytes = 16;
   if (b.cap >= bytes) return 0;
@@ -127,17 +135,6 @@ rotor h_rotor(float angle, v3 axis) {
 }
 
 const float kDeg2Rad = 3.14f / 180.0f;
-
-// centre / half extent of [mn, mx] for the conservative slab test: h is rounded up so that, in real arithmetic,
-// c - h <= mn and c + h >= mx (a zero-thickness box keeps h = 0)
-void centre_half(float mn, float mx, float *c_out, float *h_out) {
-  const float c = (float)(0.5 * ((double)mn + (double)mx));
-  const double dh = std::fmax((double)c - (double)mn, (double)mx - (double)c);
-  float h = (float)dh;
-  if ((double)h < dh) h = std::nextafterf(h, INFINITY);
-  *c_out = c;
-  *h_out = h;
-}
 
 // Per-frame constants.  Raytracing.cl:24,27,33-35,115-118 and MathLib.cl:73-74.
 void frame_setup(const b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp,
@@ -179,9 +176,9 @@ void frame_setup(const b200rt_ctx *c, const float *cam, const float *env, int wi
   F->key1 = (uint32_t)(o.seed >> 32);
 }
 
-size_t scene_smem_bytes(const b200rt_ctx *c) { return (size_t)c->n_inner * 80 + (size_t)c->n_tris * 48; }
+size_t scene_smem_bytes(const b200rt_ctx *c) { return (size_t)c->n_inner * 48 + (size_t)c->n_tris * 48; }
 
-bool use_smem_scene(const b200rt_ctx *c) { return scene_smem_bytes(c) <= kSmemSceneMax; }
+bool use_smem_scene(const b200rt_ctx *c) { return c->node_f4 == 3; }
 
 // entries of the per-lane shared-memory traversal stack: the near-first walk holds at most one entry per level;
 // trees walked in reference order keep their stack in thread-local memory instead
@@ -194,16 +191,22 @@ size_t smem_bytes(const b200rt_ctx *c, bool smem_scene) {
 void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float *d_out, KernelArgs *A) {
   A->F = F;
   SceneView &S = A->S;
-  S.nodes = static_cast<const float4 *>(c->d_nodes.p);
-  S.node_f4 = use_smem_scene(c) ? 5 : 4;
+  S.nodes = static_cast<const uint4 *>(c->d_nodes.p);
+  S.node_f4 = c->node_f4;
   S.tris = static_cast<const float4 *>(c->d_tris.p);
   S.normals = static_cast<const float4 *>(c->d_normals.p);
   S.tboxes = static_cast<const float4 *>(c->d_tboxes.p);
   S.frames = static_cast<const float4 *>(c->d_frames.p);
   S.mats = static_cast<const float *>(c->d_mats.p);
   S.bvh9 = static_cast<const float *>(c->d_bvh9.p);
+  S.leafcnt = static_cast<const int *>(c->d_leafcnt.p);
   S.root_ref = c->root_ref;
-  for (int i = 0; i < 6; ++i) S.root_ch[i] = c->root_ch[i];
+  for (int i = 0; i < 3; ++i) {
+    S.grid_base[i] = c->grid_base[i];
+    S.grid_pitch[i] = c->grid_pitch[i];
+    S.root_fc[i] = c->root_fc[i];
+    S.root_hq[i] = c->root_hq[i];
+  }
   S.cull_abs = c->cull_abs;
   S.cmax = c->cmax;
   int cap = o.stack_cap <= 0 ? 20 : (o.stack_cap > 64 ? 64 : o.stack_cap);
@@ -305,6 +308,7 @@ int prepare_trace_t(b200rt_ctx *c, WaveLaunch *w) {
   w->trace_smem = smem_bytes(c, SMEM);
   if (set_smem_attr(c, k, w->trace_smem)) return B200RT_ERR_CUDA;
   if (persistent_grid(c, k, w->trace_smem, &w->trace_grid)) return B200RT_ERR_CUDA;
+  if (c->max_trace_ctas > 0 && w->trace_grid > c->max_trace_ctas * c->sm_count) w->trace_grid = c->max_trace_ctas * c->sm_count;
   w->trace = k;
   return 0;
 }
@@ -355,6 +359,7 @@ int read_counters(b200rt_ctx *c) {
   c->stats.mismatches = h.mismatches;
   c->stats.samples = h.samples;
   c->stats.revalidated = (int32_t)(h.revalidated > 0x7fffffffull ? 0x7fffffffull : h.revalidated);
+  c->stats.exact_walks = (int32_t)(h.exact_walks > 0x7fffffffull ? 0x7fffffffull : h.exact_walks);
   float ms = 0;
   if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->stats.primary_ms = ms;
   if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->stats.trace_ms = ms;
@@ -521,6 +526,7 @@ int b200rt_create(int device, b200rt_ctx **out) {
   env_int("B200RT_QUORUM", 1, 32, &c->quorum);
   env_int("B200RT_REFILL_MIN", 1, 32, &c->refill_min);
   env_int("B200RT_TRI_QUORUM", 1, 32, &c->tri_quorum);
+  env_int("B200RT_MAX_TRACE_CTAS", 1, 32, &c->max_trace_ctas);
   auto bail = [&](const char *what, cudaError_t err) {
     fail(nullptr, B200RT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
     delete c;
@@ -540,7 +546,7 @@ void b200rt_destroy(b200rt_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_frames, &c->d_mats, &c->d_bvh9, &c->d_prim_dirk,
+  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_frames, &c->d_mats, &c->d_bvh9, &c->d_leafcnt, &c->d_prim_dirk,
                     &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b, &c->d_pA, &c->d_pB, &c->d_pC,
                     &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt};
   for (DevBuf *b : bufs)
@@ -602,186 +608,59 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
     return rc;
   }
 
+  // From here on the context describes no scene until the new one is complete: a caller that catches an error and
+  // resubmits the previous scene must not hit the content-hash shortcut above with half-replaced buffers.
+  c->have_scene = false;
+  c->have_scene_cached = false;
+  c->scene_hash = 0;
+
   const int n_nodes = (int)(n_bvh / 9), n_tris = (int)(n_face / 10);
-  const int nvp = (int)(n_vp / 3), nvn = (int)(n_vn / 3), nm = (int)(n_mat / 6);
-
-  // ---- triangles: validate indices, precompute edges exactly as MathLib.cl:129-130 rounds them -------------
-  std::vector<float4> tris((size_t)n_tris * 3), normals((size_t)n_tris), tboxes((size_t)n_tris * 2, make_float4(0, 0, 0, 0));
-  std::vector<int32_t> tri_mat((size_t)n_tris);
-  float cmax = 0.0f;
-  for (int t = 0; t < n_tris; ++t) {
-    const int32_t *f = face + 10 * (size_t)t;
-    for (int j = 7; j < 10; ++j)
-      if (f[j] < 0 || f[j] >= nvp) return fail(c, B200RT_ERR_INVALID, "triangle %d: position index %d out of range [0,%d)", t, f[j], nvp);
-    if (f[4] < 0 || f[4] >= nvn) return fail(c, B200RT_ERR_INVALID, "triangle %d: normal index %d out of range [0,%d)", t, f[4], nvn);
-    if (f[0] < 0 || f[0] >= nm) return fail(c, B200RT_ERR_INVALID, "triangle %d: material %d out of range [0,%d)", t, f[0], nm);
-    const float *a = vp + 3 * (size_t)f[7], *b = vp + 3 * (size_t)f[8], *cc = vp + 3 * (size_t)f[9];
-    v3 A = mk3(a[0], a[1], a[2]);
-    v3 e1 = mk3(b[0], b[1], b[2]) - A;
-    v3 e2 = mk3(cc[0], cc[1], cc[2]) - A;
-    tris[3 * (size_t)t + 0] = make_float4(A.x, A.y, A.z, e1.x);
-    tris[3 * (size_t)t + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
-    float matbits, rankbits;
-    int32_t m = f[0], r = 0x7fffffff;
-    memcpy(&matbits, &m, 4);
-    memcpy(&rankbits, &r, 4);
-    tris[3 * (size_t)t + 2] = make_float4(e2.z, matbits, rankbits, 0.0f);
-    const float *n0 = vn + 3 * (size_t)f[4];
-    normals[t] = make_float4(n0[0], n0[1], n0[2], 0.0f);
-    tri_mat[t] = m;
-    for (int j = 7; j < 10; ++j)
-      for (int k = 0; k < 3; ++k) {
-        float v = std::fabs(vp[3 * (size_t)f[j] + k]);
-        if (!(v <= cmax)) cmax = v;  // also catches NaN
-      }
-  }
-
-  // ---- nodes: validate, detect tree shape, rank leaves in the reference's visiting order -----------------------
-  std::vector<int> inner_id((size_t)n_nodes, -1), level((size_t)n_nodes, 0);
-  std::vector<unsigned char> seen((size_t)n_nodes, 0);
-  bool canonical = true;
-  auto L = [&](int i) { return (int)bvh[9 * (size_t)i]; };
-  auto R = [&](int i) { return (int)bvh[9 * (size_t)i + 1]; };
-  auto T = [&](int i) { return (int)bvh[9 * (size_t)i + 8]; };
+  Repacked R;
   {
-    // right-first pre-order walk == the order MathLib.cl:252-280 pops nodes when every box test passes
-    std::vector<int> stack;
-    stack.push_back(0);
-    int rank = 0, depth = 0;
-    size_t max_stack = 1;
-    while (!stack.empty()) {
-      int cur = stack.back();
-      stack.pop_back();
-      if (cur < 0 || cur >= n_nodes) return fail(c, B200RT_ERR_INVALID, "BVH child index %d out of range [0,%d)", cur, n_nodes);
-      if (seen[cur]) return fail(c, B200RT_ERR_INVALID, "BVH node %d is reachable twice: not a tree (the traversal would not terminate)", cur);
-      seen[cur] = 1;
-      int l = L(cur), r = R(cur), t = T(cur);
-      if (t < -1 || t >= n_tris) return fail(c, B200RT_ERR_INVALID, "BVH node %d: triangle %d out of range [0,%d)", cur, t, n_tris);
-      if (l < -1 || r < -1) return fail(c, B200RT_ERR_INVALID, "BVH node %d: negative child index", cur);
-      for (int k = 2; k < 8; ++k) {
-        float v = std::fabs(bvh[9 * (size_t)cur + k]);
-        if (!(v <= cmax)) cmax = v;
-      }
-      bool leaf = (t != -1 && l == -1 && r == -1), inner = (t == -1 && l != -1 && r != -1);
-      if (!leaf && !inner) canonical = false;
-      const float *bx = bvh + 9 * (size_t)cur + 2;
-      // the fast traversal's "leaf passes => ancestors pass" argument needs min <= max and child boxes nested in
-      // their parent's (rt_trace.cuh); BVH.py guarantees both, anything else is walked in reference order
-      for (int k = 0; k < 3; ++k)
-        if (!(bx[k] <= bx[k + 3])) canonical = false;
-      for (int ch : {l, r})
-        if (ch >= 0 && ch < n_nodes) {
-          const float *cb = bvh + 9 * (size_t)ch + 2;
-          for (int k = 0; k < 3; ++k)
-            if (!(cb[k] >= bx[k] && cb[k + 3] <= bx[k + 3])) canonical = false;
-        }
-      if (t != -1) {
-        int32_t old;
-        memcpy(&old, &tris[3 * (size_t)t + 2].z, 4);
-        if (old == 0x7fffffff) {
-          memcpy(&tris[3 * (size_t)t + 2].z, &rank, 4);
-          tboxes[2 * (size_t)t] = make_float4(bx[0], bx[1], bx[2], 0.0f);
-          tboxes[2 * (size_t)t + 1] = make_float4(bx[3], bx[4], bx[5], 0.0f);
-        } else {
-          canonical = false;  // a triangle held by two leaves: rank and leaf box would be ambiguous
-        }
-        ++rank;
-      }
-      if (level[cur] > depth) depth = level[cur];
-      if (l != -1) { stack.push_back(l); if (l >= 0 && l < n_nodes) level[l] = level[cur] + 1; }
-      if (r != -1) { stack.push_back(r); if (r >= 0 && r < n_nodes) level[r] = level[cur] + 1; }
-      if (stack.size() > max_stack) max_stack = stack.size();
-    }
-    c->depth = depth;
-    c->ref_stack_need = (int)max_stack;
+    std::string msg;
+    int rc = repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_mat / 6, bvh, n_bvh, &R, &msg);
+    if (rc) return fail(c, rc, "%s", msg.c_str());
   }
-  if (!(cmax < INFINITY)) return fail(c, B200RT_ERR_INVALID, "scene contains a non-finite coordinate");
-  if (c->ref_stack_need > kRefStack) canonical = false;  // closest_hit_nodrop's thread-local stack
-  // a pathologically deep tree would not leave room for the per-lane stacks in shared memory
-  if (lane_smem_bytes(c->depth + 2) > 96 * 1024) canonical = false;
-
-  // ---- repack interior nodes breadth-first into the 64-byte two-child layout --------------------------------------
-  std::vector<float4> nodes;
-  int n_inner = 0;
-  int root_ref = 0;
-  if (canonical) {
-    if (T(0) != -1) {
-      root_ref = ~T(0);
-    } else {
-      std::vector<int> order;
-      order.reserve((size_t)n_nodes / 2 + 1);
-      order.push_back(0);
-      inner_id[0] = 0;
-      for (size_t q = 0; q < order.size(); ++q) {
-        int cur = order[q];
-        int ch[2] = {L(cur), R(cur)};
-        for (int k = 0; k < 2; ++k)
-          if (T(ch[k]) == -1) {
-            inner_id[ch[k]] = (int)order.size();
-            order.push_back(ch[k]);
-          }
-      }
-      n_inner = (int)order.size();
-      // small scenes are staged in shared memory with 80-byte node spacing (SceneView::node_f4)
-      const size_t nf4 = ((size_t)n_inner * 80 + (size_t)n_tris * 48 <= kSmemSceneMax) ? 5 : 4;
-      nodes.assign((size_t)n_inner * nf4, make_float4(0, 0, 0, 0));
-      for (int q = 0; q < n_inner; ++q) {
-        int cur = order[q];
-        int l = L(cur), r = R(cur);
-        const float *bl = bvh + 9 * (size_t)l, *br = bvh + 9 * (size_t)r;
-        // interior refs are float4 offsets into the node array (index x floats4-per-node)
-        int32_t refl = T(l) != -1 ? ~T(l) : (int32_t)(inner_id[l] * (int)nf4);
-        int32_t refr = T(r) != -1 ? ~T(r) : (int32_t)(inner_id[r] * (int)nf4);
-        float fl, fr;
-        memcpy(&fl, &refl, 4);
-        memcpy(&fr, &refr, 4);
-        float cl[3], hl[3], cr[3], hr[3];
-        for (int k = 0; k < 3; ++k) {
-          centre_half(bl[2 + k], bl[5 + k], &cl[k], &hl[k]);
-          centre_half(br[2 + k], br[5 + k], &cr[k], &hr[k]);
-        }
-        nodes[nf4 * (size_t)q + 0] = make_float4(cl[0], cl[1], cl[2], hl[0]);
-        nodes[nf4 * (size_t)q + 1] = make_float4(hl[1], hl[2], cr[0], cr[1]);
-        nodes[nf4 * (size_t)q + 2] = make_float4(cr[2], hr[0], hr[1], hr[2]);
-        nodes[nf4 * (size_t)q + 3] = make_float4(fl, fr, 0.0f, 0.0f);
-      }
-    }
-  }
-  for (int k = 0; k < 3; ++k) centre_half(bvh[2 + k], bvh[5 + k], &c->root_ch[k], &c->root_ch[3 + k]);
-  {
-    float dx = bvh[5] - bvh[2], dy = bvh[6] - bvh[3], dz = bvh[7] - bvh[4];
-    c->cull_abs = 1e-3f * std::sqrt(dx * dx + dy * dy + dz * dz);
-  }
-  c->cmax = cmax;
-  // range the conservative slab test's error margin is proven for (rt_trace.cuh); outside it every ray takes
-  // closest_hit_nodrop
-  c->fast_ok = (cmax <= 1.099511627776e12f /* 2^40 */ && cmax >= 9.5367431640625e-07f /* 2^-20 */) ? 1 : 0;
 
   // ---- upload -------------------------------------------------------------------------------------------------------------
   CU(cudaSetDevice(c->device));
-  if (ensure(c, c->d_tris, tris.size() * sizeof(float4))) return B200RT_ERR_CUDA;
-  if (ensure(c, c->d_normals, normals.size() * sizeof(float4))) return B200RT_ERR_CUDA;
-  if (ensure(c, c->d_tboxes, tboxes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tris, R.tris.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_normals, R.normals.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_tboxes, R.tboxes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_frames, (size_t)n_tris * kFrameVec * sizeof(float4))) return B200RT_ERR_CUDA;
-  if (ensure(c, c->d_nodes, nodes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_nodes, R.nodes.size() * sizeof(uint4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_bvh9, (size_t)n_bvh * 4)) return B200RT_ERR_CUDA;
-  CU(cudaMemcpyAsync(c->d_tris.p, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_normals.p, normals.data(), normals.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_tboxes.p, tboxes.data(), tboxes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  if (!nodes.empty())
-    CU(cudaMemcpyAsync(c->d_nodes.p, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  if (ensure(c, c->d_leafcnt, R.leaf_count.size() * sizeof(int32_t))) return B200RT_ERR_CUDA;
+  CU(cudaMemcpyAsync(c->d_leafcnt.p, R.leaf_count.data(), R.leaf_count.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_tris.p, R.tris.data(), R.tris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_normals.p, R.normals.data(), R.normals.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_tboxes.p, R.tboxes.data(), R.tboxes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  if (!R.nodes.empty())
+    CU(cudaMemcpyAsync(c->d_nodes.p, R.nodes.data(), R.nodes.size() * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_bvh9.p, bvh, (size_t)n_bvh * 4, cudaMemcpyHostToDevice, c->stream));
   k_tri_frames<<<(n_tris + 127) / 128, 128, 0, c->stream>>>(static_cast<const float4 *>(c->d_normals.p), n_tris,
                                                            static_cast<float4 *>(c->d_frames.p));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
+  // ---- commit: every field the kernels' launch geometry and margins derive from, together ----------------------------
   c->n_nodes9 = n_nodes;
-  c->n_inner = n_inner;
+  c->n_inner = R.n_inner;
   c->n_tris = n_tris;
-  c->canonical = canonical;
-  c->root_ref = root_ref;
-  c->tri_mat.swap(tri_mat);
-  c->have_scene = false;
+  c->node_f4 = R.node_f4;
+  c->depth = R.depth;
+  c->ref_stack_need = R.ref_stack_need;
+  c->canonical = R.canonical;
+  c->root_ref = R.root_ref;
+  for (int k = 0; k < 3; ++k) {
+    c->grid_base[k] = R.grid_base[k];
+    c->grid_pitch[k] = R.grid_pitch[k];
+    c->root_fc[k] = R.root_fc[k];
+    c->root_hq[k] = R.root_hq[k];
+  }
+  c->cull_abs = R.cull_abs;
+  c->cmax = R.cmax;
+  c->fast_ok = R.fast_ok;
+  c->tri_mat.swap(R.tri_mat);
   c->mat_hash = 0;
   c->n_mats = 0;
   int rc = b200rt_set_materials(c, mat, n_mat);
@@ -789,6 +668,8 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   c->have_scene = true;
   c->have_scene_cached = true;
   c->scene_hash = h;
+  c->stats.repack_ms = (float)(R.ms_tris + R.ms_walk + R.ms_nodes);
+  c->stats.ref_stack_need = c->ref_stack_need;
   c->stats.nodes = n_nodes;
   c->stats.triangles = n_tris;
   c->stats.bvh_depth = c->depth;

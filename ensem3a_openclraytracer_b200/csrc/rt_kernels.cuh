@@ -22,9 +22,10 @@ namespace b200rt {
 constexpr int kBlock = 128;        // k_primary, k_trace, k_trace_rays
 constexpr int kShadeBlock = 128;
 constexpr unsigned kChunk = 32;    // rays a warp claims from the list per atomic
+constexpr int kHitNeedsExactWalk = -2;  // pHit.x of a ray k_trace did not walk (see k_trace); k_shade walks it exactly
 
 struct DeviceCounters {
-  unsigned long long rays, box_tests, tri_tests, mismatches, samples, revalidated;
+  unsigned long long rays, box_tests, tri_tests, mismatches, samples, revalidated, exact_walks;
 };
 
 // path state, one entry per pixel:
@@ -80,7 +81,7 @@ RT_DEV SceneView stage_scene(const KernelArgs &A, unsigned char *smem, size_t *u
   }
   __shared__ __align__(8) uint64_t bar;
   const uint32_t nb = (uint32_t)A.n_nodes * 16u * (uint32_t)A.S.node_f4, tb = (uint32_t)A.n_tris * 48u;
-  float4 *s_nodes = reinterpret_cast<float4 *>(smem);
+  uint4 *s_nodes = reinterpret_cast<uint4 *>(smem);
   float4 *s_tris = reinterpret_cast<float4 *>(smem + nb);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
   unsigned int *n_out = A.cnt + iter + 1;
   const unsigned int lane = threadIdx.x & 31u;
   unsigned long long samples = 0;
-  unsigned int reval = 0;
+  unsigned int reval = 0, exact = 0;
   const unsigned int warps = (gridDim.x * kShadeBlock) >> 5;
   for (unsigned int tb = ((blockIdx.x * kShadeBlock + threadIdx.x) >> 5) << 5; tb < n_in; tb += warps << 5) {
     const unsigned int t = tb + lane;
@@ -267,13 +268,14 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     bool pixel_done = false, start = valid && first, shade = false, end_sample = false, sun_done = false;
 
     // ---- phase 1: the winner of the conservative walk must pass the exact leaf-box test ---------------------------------
-    if (valid && !first && A.validate && htri >= 0) {
+    if (valid && !first && A.validate && htri != -1) {
       const v3 dray = sun_ray ? F.sun_dir : d;
-      if (!validate_hit(S, o, dray, htri)) {  // grazing ray: re-trace exactly
+      if (htri == kHitNeedsExactWalk ||
+          !validate_winner(S, o, dray, htri, __float_as_int(__ldg(S.tris + 3 * (size_t)htri + 2).z))) {  // out-of-range or grazing ray: re-trace exactly
         const Hit h = closest_hit_nodrop<false>(S, o, dray);
+        if (htri != kHitNeedsExactWalk) ++reval; else ++exact;
         htri = h.tri;
         hk = h.k;
-        ++reval;
       }
     }
     __syncwarp();
@@ -404,10 +406,12 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
   for (int o = 16; o > 0; o >>= 1) {
     samples += __shfl_down_sync(0xffffffffu, samples, o);
     reval += __shfl_down_sync(0xffffffffu, reval, o);
+    exact += __shfl_down_sync(0xffffffffu, exact, o);
   }
   if (lane == 0) {
     if (samples) atomicAdd(&A.counters->samples, samples);
     if (reval) atomicAdd(&A.counters->revalidated, (unsigned long long)reval);
+    if (exact) atomicAdd(&A.counters->exact_walks, (unsigned long long)exact);
   }
 }
 
@@ -422,8 +426,11 @@ __global__ void k_tri_frames(const float4 *__restrict__ normals, int n_tris, flo
 }
 
 // ---- tracing ------------------------------------------------------------------------------------------------------
+#ifndef B200RT_TRACE_MINB
+#define B200RT_TRACE_MINB 1
+#endif
 template <int TRAV, bool SMEM, bool STATS>
-__global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ KernelArgs A, int iter) {
+__global__ void __launch_bounds__(kBlock, B200RT_TRACE_MINB) k_trace(const __grid_constant__ KernelArgs A, int iter) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned int n = A.cnt[iter + 1];
   if (n == 0u) return;
@@ -439,10 +446,9 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
   const unsigned int lt_mask = (1u << lane) - 1u;
 
   Trav T;
-  T.active = false;
-  T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0x7fffffff; T.lim = 0.0f; T.cur = 0; T.sp = 0;
+  T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0x7fffffff; T.lim = 0.0f; T.cur = -1; T.sp = 0;
   T.o = mk3(0, 0, 0); T.d = mk3(1, 1, 1);
-  T.Q.r = mk3(1, 1, 1); T.Q.kn = mk3(0, 0, 0); T.Q.kf = mk3(0, 0, 0);
+  T.Q.A = mk3(1, 1, 1); T.Q.Bn = mk3(0, 0, 0); T.Q.Bf = mk3(0, 0, 0);
   int pn = 0;         // parked leaves of this lane
   int path = -1;      // path whose ray this lane is tracing
   unsigned int c_next = 0, c_end = 0;  // the warp's claimed chunk of the list (uniform)
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
   for (;;) {
     // ---- node phase: one node per lane per turn -----------------------------------------------------------------------------
     for (;;) {
-      const bool can = T.active && pn <= kParkCap - 2;
+      const bool can = trav_active(T) && pn <= kParkCap - 2;
       if (__popc(__ballot_sync(0xffffffffu, can)) < thresh) break;
       if (can) trav_step<SMEM, STATS>(S, T, pn, parks, kBlock, st, &tc);
     }
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
       if (__popc(pm) < A.tri_quorum) break;
     }
     // ---- finished rays are handed back; idle lanes pull the next rays together ---------------------------------------------------
-    const bool finished = (path >= 0) && !T.active && pn == 0;
+    const bool finished = (path >= 0) && !trav_active(T) && pn == 0;
     if (finished) {
       A.pHit[path] = make_int2(T.best.tri, __float_as_int(T.best.k));
       path = -1;
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
     const int n_idle = __popc(idle);
     if (n_idle == 0) continue;
     if (n_idle < A.refill_min &&
-        __popc(__ballot_sync(0xffffffffu, T.active && pn <= kParkCap - 2)) >= A.quorum)
+        __popc(__ballot_sync(0xffffffffu, trav_active(T) && pn <= kParkCap - 2)) >= A.quorum)
       continue;  // enough lanes can still step: let more finish before paying for a refill
     {
       int need = n_idle;
@@ -508,12 +514,20 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
           const v3 o = mk3(sa.x, sa.y, sa.z);
           const v3 d = ((__float_as_uint(sb.z) >> 3) & 1u) ? A.F.sun_dir : mk3(sa.w, sb.x, sb.y);
           rays++;
-          if (TRAV == 0 && ray_is_fast(S, o, d)) {
-            trav_begin<SMEM, STATS>(S, T, o, d, pn, parks, &tc);
-          } else {  // reference / verify traversal, or a ray the conservative test is not proven for: whole walk at once
-            T.best = (TRAV == 0) ? closest_hit_nodrop<SMEM>(S, o, d)
-                                 : closest_hit<TRAV, SMEM, STATS>(S, o, d, st, parks, kBlock, &tc, &mism);
-            T.active = false;
+          if (TRAV == 0) {
+            if (ray_is_fast(S, o)) {
+              trav_begin<SMEM, STATS>(S, T, o, d, pn, parks, &tc);
+            } else {
+              // the margins of the conservative test are not proven for this origin / scene (|coordinate| > 2^40):
+              // k_shade's validation phase walks the ray exactly (closest_hit_nodrop), which keeps that walk's
+              // registers and local stack out of this kernel
+              T.best.tri = kHitNeedsExactWalk;
+              T.best.k = 1000.0f;
+              T.cur = -1;
+            }
+          } else {  // reference / verify traversal: whole walk at once
+            T.best = closest_hit<TRAV, SMEM, STATS>(S, o, d, st, parks, kBlock, &tc, &mism);
+            T.cur = -1;
           }
         }
         rank -= take;

@@ -34,24 +34,35 @@
 #pragma once
 #include "rt_math.cuh"
 
+#ifndef B200RT_PREFETCH
+#define B200RT_PREFETCH 0
+#endif
+
 namespace b200rt {
 
 // ---- repacked scene -------------------------------------------------------------------------------
-// node (4 x float4; 64 B apart in global memory, 80 B apart when the scene is staged in shared memory so that
-// lanes reading different nodes spread over all 32 banks), interior nodes only, breadth-first, root = 0:
-//   q0 = Lc.x Lc.y Lc.z Lh.x        c = box centre, h = half extent, rounded so that [c - h, c + h] encloses
-//   q1 = Lh.y Lh.z Rc.x Rc.y        the child's exact [min, max] (these boxes only cull; exactness lives in the
-//   q2 = Rc.z Rh.x Rh.y Rh.z        leaf boxes of `tboxes` and in the as-is array `bvh9`)
-//   q3 = refL refR (int bits)  -  -        ref >= 0: float4 offset of an interior node (index x node_f4),
-//                                          ref < 0: leaf of triangle ~ref
+// node (32 B = 8 words, ONE 256-bit load per visit; 32 B apart in global memory, 48 B apart when the scene is
+// staged in shared memory so that lanes reading different nodes spread over all bank groups), interior nodes only,
+// root = 0.  A record holds the boxes of BOTH children, quantised onto a 2^15 grid spanning the root box:
+//   w0 = Lcx|Lcy   w1 = Lcz|Rcx   w2 = Rcy|Rcz      centre, 15-bit grid index q per axis (hi|lo 16-bit halves)
+//   w3 = Lhx|Lhy   w4 = Lhz|Rhx   w5 = Rhy|Rhz      half extent / grid pitch, upper 16 bits of a binary32 (rounded up)
+//   w6 = refL      w7 = refR                        ref >= 0: float4 offset of an interior node (index x node_f4),
+//                                                   ref < 0: leaf of triangle ~ref
+// Decoding costs one instruction per value and no conversion: PRMT places q in mantissa bits 22..8 under the
+// exponent of 0.5, giving the binary32 fc = 0.5 + q / 65536 exactly; `w & 0xffff0000` / `w << 16` are the half
+// extents.  In real arithmetic the decoded box is  c = grid_base + fc * grid_pitch,  h = hq * grid_pitch  per axis,
+// and b200rt_set_scene chooses q and hq so that [c - h, c + h] ENCLOSES the child's exact float32 [min, max] (checked
+// there in binary64).  These boxes only cull; exactness lives in the leaf boxes of `tboxes` and in the as-is array
+// `bvh9`.  Against the round-1 record (two boxes as 12 floats, 64 B, two 256-bit loads) this halves the L1 /
+// L2 / HBM bytes and the L1 wavefronts of every node visit; ncu had the L1TEX data pipe of k_trace at 83 %.
 // triangle (48 B, 3 x float4):
 //   t0 = A.x A.y A.z e1.x     t1 = e1.y e1.z e2.x e2.y     t2 = e2.z mat rank -   (mat, rank int bits)
 //   with e1 = B - A, e2 = C - A rounded exactly as MathLib.cl:129-130 rounds them.
 // normal (16 B): first-vertex normal of the triangle (MathLib.cl:151), w unused.
 // leaf box (32 B, 2 x float4): min.xyz -, max.xyz -   of the leaf that holds the triangle (validate_hit).
 struct SceneView {
-  const float4 *nodes;
-  int node_f4;              // float4 per node: 4, or 5 for a scene small enough to be staged in shared memory
+  const uint4 *nodes;
+  int node_f4;              // 16-byte units per node: 2, or 3 for a scene small enough to be staged in shared memory
   const float4 *tris;
   const float4 *normals;
   const float4 *tboxes;
@@ -59,10 +70,14 @@ struct SceneView {
   const float *mats;        // 6 floats per material
   // as-is reference buffers for closest_hit_reference
   const float *bvh9;
+  const int *leafcnt;       // leaves in the sub-tree of each node of bvh9 (validate_chain)
   int root_ref;             // ~tri when the whole tree is one leaf
-  float root_ch[6];         // centre xyz, half extent xyz of node 0 (enclosing, like the node records)
+  float grid_base[3];       // decoded centre = grid_base + fc * grid_pitch   (fc in [0.5, 1))
+  float grid_pitch[3];
+  float root_fc[3];         // node 0's box in the units of the node records (enclosing, like them)
+  float root_hq[3];
   float cull_abs;           // absolute part of the culling margin (1e-3 x scene diagonal)
-  float cmax;               // largest |coordinate| of any box plane
+  float cmax;               // largest |coordinate| of any box plane, vertex or grid point
   int stack_cap;            // reference traversal
   int fast_ok;              // scene coordinates in the range the conservative test is proven for
 };
@@ -82,22 +97,24 @@ RT_DEV float4 ld4(const float4 *p) {
   return __ldg(p);
 }
 
-// One node = 64 contiguous bytes.  From global memory it is fetched with two 256-bit loads (LDG.E.256, sm_100+):
-// lanes of a warp sit at unrelated nodes, so the L1 cost of a node visit is one wavefront per lane per load
-// instruction, and two loads instead of four halve it.
+// One node = 32 contiguous bytes: one 256-bit load from global memory (LDG.E.256, sm_100+), two 128-bit loads from
+// shared memory.  Lanes of a warp sit at unrelated nodes, so the L1 cost of a node visit is one wavefront per lane
+// per load instruction.
 template <bool SMEM>
-RT_DEV void ld_node(const float4 *p, float4 &q0, float4 &q1, float4 &q2, float4 &q3) {
+RT_DEV void ld_node(const uint4 *p, uint4 &a, uint4 &b) {
   if (SMEM) {
-    q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
+    a = p[0]; b = p[1];
   } else {
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w)
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
         : "l"(p));
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w)
-        : "l"(p + 2));
   }
 }
+
+RT_DEV float fc_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3f000000u, 0x7324)); }  // 0.5 + (w >> 16) / 65536
+RT_DEV float fc_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3f000000u, 0x7104)); }  // 0.5 + (w & 0xffff) / 65536
+RT_DEV float hq_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+RT_DEV float hq_lo(uint32_t w) { return __uint_as_float(w << 16); }
 
 // ---- exact slab test, MathLib.cl:169-188 --------------------------------------------------------------
 RT_DEV bool slab_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float *tmin,
@@ -116,20 +133,24 @@ RT_DEV bool slab_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, f
 }
 
 // ---- conservative slab test ----------------------------------------------------------------------------
-// Boxes are held as centre c and half extent h with [c - h, c + h] enclosing the exact [min, max].  Per ray:
-// r = RN(1/d) and two constants per axis, kn = RN(-o·r) - m and kf = RN(-o·r) + m, so that
-//     near = fma(-h, |r|, fma(c, r, kn))  <=  min(t_exact(min), t_exact(max))
-//     far  = fma(+h, |r|, fma(c, r, kf))  >=  max(t_exact(min), t_exact(max)),     t_exact(p) = RN(RN(p - o) / d).
-// Only the FMA pipe is used: no per-axis min / max is needed because |r| orders the two planes; the three
-// `near` values and the three `far` values are then reduced with one 3-input max / min each.
-// Error budget, with P = max(|c| + h, |o|) and u = 2^-24:  t_exact differs from the real (p - o)/d by at most
-// 4u·P|1/d| (two roundings of a value of magnitude <= 2P/|d|);  the FMA chain differs from the real
-// (c -+ h - o)/d by at most  2u·P|r| (r)  +  u·P|r| (o·r)  +  u·(P|r| + m) (kn / kf)  +  2u·P|r| (inner FMA)
-// +  2u·P|r| (outer FMA)  <  9u·P|r|.  The margin  m = 2^-19 (cmax + |o|) |r| = 32u (cmax + |o|) |r|  covers the
-// sum (13u·P|r|) more than twice.  Valid while every |d| component lies in [2^-40, 2^40] and |o|, cmax <= 2^40
-// (no overflow, no denormal r).
+// A box is held as (fc, hq) per axis, meaning centre c = base + fc * pitch and half extent h = hq * pitch in real
+// arithmetic, with [c - h, c + h] enclosing the exact [min, max].  Per ray and axis: r = RN(1/d),
+//     A = RN(pitch * r),   B = RN(RN(base - o) * r),   Bn = B - m,   Bf = B + m,
+//     near = fma(-hq, |A|, fma(fc, A, Bn)),   far = fma(+hq, |A|, fma(fc, A, Bf))
+// — FMAs only, no per-axis min / max because |A| orders the two planes.  The three `near` and the three `far` values
+// are reduced with one 3-input max / min each to lo and hi.
+// Error budget per axis, in units of u (cmax + |o|) |r| with u = 2^-24.  b200rt_set_scene makes cmax bound every
+// |box plane|, |vertex coordinate|, |base| and |base + pitch|, hence pitch <= 2 cmax and |c| <= cmax for every decoded
+// centre.  A = RN(pitch·r), scaled by fc < 1: 2.  B: one rounding of base - o (<= cmax + |o|) and one of the product: 2.
+// Bn / Bf: 1.  r against 1/d: 1.  Inner FMA: 1 (|result| <= (cmax + |o|)|r| + m).  Outer FMA: 2 (|result| <= (2 cmax + |o|)|r| + m).
+// hq·|A| against h·|r|, where hq·pitch >= h exactly and |A| >= pitch |r| (1 - 2u): 2.  Together 11.  The reference's own
+// t = RN(RN(p - o) / d) is within 2 of the real (p - o)/d.  The margin, PER AXIS (a ray with one tiny direction
+// component must not lose the culling of the other two axes),
+//     m = 2^-18 (cmax + |o|) |r|        (= 64 units, five times the sum of 13),
+// gives  lo <= tmin_exact  and  hi >= tmax_exact: the box certainly fails the reference's test when hi < lo.
+// Valid while every |d| component lies in [2^-40, 2^40] and |o|, cmax <= 2^40 (no overflow, no denormal r).
 struct RayFast {
-  v3 r, kn, kf;
+  v3 A, Bn, Bf;
 };
 
 RT_DEV bool comp_ok(float d) {
@@ -137,37 +158,65 @@ RT_DEV bool comp_ok(float d) {
   return a >= 9.094947017729282e-13f /* 2^-40 */ && a <= 1.099511627776e12f /* 2^40 */;
 }
 
-RT_DEV bool ray_is_fast(const SceneView &S, v3 o, v3 d) {
-  return S.fast_ok != 0 && comp_ok(d.x) && comp_ok(d.y) && comp_ok(d.z) && fabsf(o.x) <= 1.099511627776e12f &&
-         fabsf(o.y) <= 1.099511627776e12f && fabsf(o.z) <= 1.099511627776e12f;
+// every direction component is a non-zero finite number of moderate size: "the leaf box passes => every ancestor
+// box passes" holds and validate_hit decides; otherwise validate_chain does
+RT_DEV bool ray_is_regular(v3 d) { return comp_ok(d.x) && comp_ok(d.y) && comp_ok(d.z); }
+
+// the conservative traversal applies (any direction; the scene and the origin are in the range the margins are proven for)
+RT_DEV bool ray_is_fast(const SceneView &S, v3 o) {
+  return S.fast_ok != 0 && fabsf(o.x) <= 1.099511627776e12f && fabsf(o.y) <= 1.099511627776e12f &&
+         fabsf(o.z) <= 1.099511627776e12f;
 }
 
-RT_DEV void rayfast_axis(float o, float d, float cmax, float *r, float *kn, float *kf) {
-  const float rr = __frcp_rn(d);
-  const float t0 = -(o * rr);
-  const float m = (1.9073486328125e-06f /* 2^-19 */ * (cmax + fabsf(o))) * fabsf(rr);
-  *r = rr;
-  *kn = t0 - m;
-  *kf = t0 + m;
+// Irregular axes (ray_is_regular fails; the reference's test then involves infinities and NaNs, MathLib.cl:169-188):
+//   * |d| < 2^-40, zero and denormals included: the ray's coordinate on this axis is practically constant.  The axis is
+//     tested as if r were +-2^40 with the margin enlarged by 1002 + 2 cull_abs: a box whose (decoded) slab holds the
+//     origin's coordinate gets an interval that covers [-cull_abs, 1001 + cull_abs] — everything the traversal can
+//     still be interested in, so no constraint — and a slab further than ~2^-18 (cmax + |o|) from the coordinate fails,
+//     as it does in the reference (both quotients +inf or both -inf, or beyond every distance of interest).
+//   * |d| > 2^40, infinite or NaN: no constraint (A = 0, Bn = -inf, Bf = +inf give near = -inf, far = +inf).
+// Either way the reference can only be stricter, so the traversal still visits a superset of the candidates;
+// validate_chain then decides whether the winner is one.
+RT_DEV void rayfast_axis(float o, float d, float cmax, float cull_abs, float base, float pitch, float *A, float *Bn,
+                         float *Bf) {
+  const float a = fabsf(d);
+  float rr, extra = 0.0f;
+  if (a >= 9.094947017729282e-13f /* 2^-40 */ && a <= 1.099511627776e12f /* 2^40 */) {
+    rr = __frcp_rn(d);
+  } else if (a < 9.094947017729282e-13f) {
+    rr = copysignf(1.099511627776e12f, d);
+    extra = 1002.0f + 2.0f * cull_abs;
+  } else {
+    *A = 0.0f;
+    *Bn = -INFINITY;
+    *Bf = INFINITY;
+    return;
+  }
+  const float b = (base - o) * rr;
+  const float m = (3.814697265625e-06f /* 2^-18 */ * (cmax + fabsf(o))) * fabsf(rr) + extra;
+  *A = pitch * rr;
+  *Bn = b - m;
+  *Bf = b + m;
 }
 
 RT_DEV RayFast make_rayfast(const SceneView &S, v3 o, v3 d) {
   RayFast Q;
-  rayfast_axis(o.x, d.x, S.cmax, &Q.r.x, &Q.kn.x, &Q.kf.x);
-  rayfast_axis(o.y, d.y, S.cmax, &Q.r.y, &Q.kn.y, &Q.kf.y);
-  rayfast_axis(o.z, d.z, S.cmax, &Q.r.z, &Q.kn.z, &Q.kf.z);
+  rayfast_axis(o.x, d.x, S.cmax, S.cull_abs, S.grid_base[0], S.grid_pitch[0], &Q.A.x, &Q.Bn.x, &Q.Bf.x);
+  rayfast_axis(o.y, d.y, S.cmax, S.cull_abs, S.grid_base[1], S.grid_pitch[1], &Q.A.y, &Q.Bn.y, &Q.Bf.y);
+  rayfast_axis(o.z, d.z, S.cmax, S.cull_abs, S.grid_base[2], S.grid_pitch[2], &Q.A.z, &Q.Bn.z, &Q.Bf.z);
   return Q;
 }
 
-// lo <= tmin_exact and hi >= tmax_exact of the box enclosed by (c, h); the box certainly fails when hi < lo
-RT_DEV void slab_cons(const RayFast &Q, float cx, float cy, float cz, float hx, float hy, float hz, float *lo,
+// lo <= tmin_exact and hi >= tmax_exact of the box enclosed by (fc, hq); the box certainly fails when hi < lo
+RT_DEV void slab_cons(const RayFast &Q, float fcx, float fcy, float fcz, float hx, float hy, float hz, float *lo,
                       float *hi) {
-  const float nx = __fmaf_rn(-hx, fabsf(Q.r.x), __fmaf_rn(cx, Q.r.x, Q.kn.x));
-  const float ny = __fmaf_rn(-hy, fabsf(Q.r.y), __fmaf_rn(cy, Q.r.y, Q.kn.y));
-  const float nz = __fmaf_rn(-hz, fabsf(Q.r.z), __fmaf_rn(cz, Q.r.z, Q.kn.z));
-  const float fx = __fmaf_rn(hx, fabsf(Q.r.x), __fmaf_rn(cx, Q.r.x, Q.kf.x));
-  const float fy = __fmaf_rn(hy, fabsf(Q.r.y), __fmaf_rn(cy, Q.r.y, Q.kf.y));
-  const float fz = __fmaf_rn(hz, fabsf(Q.r.z), __fmaf_rn(cz, Q.r.z, Q.kf.z));
+  const float ax = fabsf(Q.A.x), ay = fabsf(Q.A.y), az = fabsf(Q.A.z);
+  const float nx = __fmaf_rn(-hx, ax, __fmaf_rn(fcx, Q.A.x, Q.Bn.x));
+  const float ny = __fmaf_rn(-hy, ay, __fmaf_rn(fcy, Q.A.y, Q.Bn.y));
+  const float nz = __fmaf_rn(-hz, az, __fmaf_rn(fcz, Q.A.z, Q.Bn.z));
+  const float fx = __fmaf_rn(hx, ax, __fmaf_rn(fcx, Q.A.x, Q.Bf.x));
+  const float fy = __fmaf_rn(hy, ay, __fmaf_rn(fcy, Q.A.y, Q.Bf.y));
+  const float fz = __fmaf_rn(hz, az, __fmaf_rn(fcz, Q.A.z, Q.Bf.z));
   *lo = fmaxf(fmaxf(nx, ny), nz);
   *hi = fminf(fminf(fx, fy), fz);
 }
@@ -211,6 +260,38 @@ RT_DEV bool validate_hit(const SceneView &S, v3 o, v3 d, int tri) {
   const float4 mn = __ldg(S.tboxes + 2 * (size_t)tri), mx = __ldg(S.tboxes + 2 * (size_t)tri + 1);
   float lo, hi;
   return slab_exact(o, d, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, &lo, &hi);
+}
+
+// The reference accepts a triangle only if the exact slab test passes for its leaf box AND every ancestor box.  For
+// a regular ray the leaf implies the ancestors (see the top of this file).  With a zero direction component the test
+// involves (b - o) / 0: a plane the origin lies exactly on gives 0/0 = NaN, which fmin / fmax drop, and then an
+// ancestor whose plane coincides with the origin's coordinate can fail although a (zero-thickness) leaf passes.  So
+// for such rays the winner's whole root-to-leaf chain is put through the exact test: one descent without a stack,
+// steered by the leaf's rank in the reference's visiting order (right sub-tree first, MathLib.cl:275-280) and the
+// number of leaves under each node.  Canonical trees only (two children per interior node).
+__device__ __noinline__ bool validate_chain(const SceneView &S, v3 o, v3 d, int tri, int rank) {
+  int node = 0, first = 0;   // ranks [first, first + leafcnt[node]) live under `node`
+  for (;;) {
+    const float *n = S.bvh9 + 9 * (size_t)node;
+    float lo, hi;
+    if (!slab_exact(o, d, __ldg(n + 2), __ldg(n + 3), __ldg(n + 4), __ldg(n + 5), __ldg(n + 6), __ldg(n + 7), &lo, &hi))
+      return false;
+    const int t = (int)__ldg(n + 8);
+    if (t != -1) return t == tri;
+    const int l = (int)__ldg(n), r = (int)__ldg(n + 1);
+    const int under_r = __ldg(S.leafcnt + r);
+    if (rank < first + under_r) {
+      node = r;
+    } else {
+      first += under_r;
+      node = l;
+    }
+  }
+}
+
+// the winner of the conservative walk (triangle `tri`, visiting rank `rank`) is the reference's hit iff this holds
+RT_DEV bool validate_winner(const SceneView &S, v3 o, v3 d, int tri, int rank) {
+  return ray_is_regular(d) ? validate_hit(S, o, d, tri) : validate_chain(S, o, d, tri, rank);
 }
 
 // ---- reference-order traversal ---------------------------------------------------------------------------
@@ -280,11 +361,12 @@ struct Trav {
   Hit best;
   int best_rank;
   float lim;     // sub-trees whose conservative entry distance exceeds this cannot hold a closer hit
-  int cur, sp;   // cur: float4 offset of the node to visit next
-  bool active;
+  int cur, sp;   // cur: 16-byte offset of the node to visit next; < 0: the walk has ended
 };
 
-RT_DEV float cull_limit(const SceneView &S, float best_k) { return best_k * 1.001f + S.cull_abs; }
+RT_DEV bool trav_active(const Trav &T) { return T.cur >= 0; }
+
+RT_DEV float cull_limit(const SceneView &S, const Trav &T) { return __fmaf_rn(T.best.k, 1.001f, S.cull_abs); }
 
 // Leaves whose box passes the conservative test are not tested on the spot (only a few lanes of a warp reach a
 // leaf in the same turn) but parked, at most kParkCap per lane (entry e of lane l at parks[e * stride]); the
@@ -299,17 +381,17 @@ RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, int &pn, uint32_
   T.best.tri = -1;
   T.best.k = 1000.0f;
   T.best_rank = 0x7fffffff;
-  T.lim = cull_limit(S, T.best.k);
-  T.cur = 0;
+  T.lim = cull_limit(S, T);
   T.sp = 0;
   float lo, hi;
   if (STATS) cnt->box_tests++;
-  slab_cons(T.Q, S.root_ch[0], S.root_ch[1], S.root_ch[2], S.root_ch[3], S.root_ch[4], S.root_ch[5], &lo, &hi);
-  T.active = hi >= lo;
-  if (T.active && S.root_ref < 0) {
+  slab_cons(T.Q, S.root_fc[0], S.root_fc[1], S.root_fc[2], S.root_hq[0], S.root_hq[1], S.root_hq[2], &lo, &hi);
+  const bool go = hi >= lo;
+  T.cur = go ? 0 : -1;
+  if (go && S.root_ref < 0) {
     parks[0] = (uint32_t)S.root_ref;
     pn = 1;
-    T.active = false;
+    T.cur = -1;
   }
 }
 
@@ -318,13 +400,24 @@ RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, int &pn, uint32_
 template <bool SMEM, bool STATS>
 RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int pstride, LaneStack st,
                       TraceCounters *cnt) {
-  float4 q0, q1, q2, q3;
-  ld_node<SMEM>(S.nodes + T.cur, q0, q1, q2, q3);
-  const int refL = __float_as_int(q3.x), refR = __float_as_int(q3.y);
+  uint4 wa, wb;
+  ld_node<SMEM>(S.nodes + T.cur, wa, wb);
+  const int refL = (int)wb.z, refR = (int)wb.w;
+#if B200RT_PREFETCH
+  if (!SMEM) {  // experiment: start fetching both children's records while this node's boxes are tested
+#if B200RT_PREFETCH == 1
+#define B200RT_PF "prefetch.global.L1 [%0];"
+#else
+#define B200RT_PF "prefetch.global.L2 [%0];"
+#endif
+    if (refL >= 0) asm volatile(B200RT_PF ::"l"(S.nodes + refL));
+    if (refR >= 0) asm volatile(B200RT_PF ::"l"(S.nodes + refR));
+  }
+#endif
   float loL, hiL, loR, hiR;
   if (STATS) cnt->box_tests += 2;
-  slab_cons(T.Q, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &loL, &hiL);
-  slab_cons(T.Q, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &loR, &hiR);
+  slab_cons(T.Q, fc_hi(wa.x), fc_lo(wa.x), fc_hi(wa.y), hq_hi(wa.w), hq_lo(wa.w), hq_hi(wb.x), &loL, &hiL);
+  slab_cons(T.Q, fc_lo(wa.y), fc_hi(wa.z), fc_lo(wa.z), hq_lo(wb.x), hq_hi(wb.y), hq_lo(wb.y), &loR, &hiR);
   const float lim = T.lim;
   const float behind = -S.cull_abs;
   const bool goL = hiL >= loL && !(loL > lim) && !(hiL < behind);
@@ -344,17 +437,15 @@ RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int
   } else if (inL || inR) {
     T.cur = inL ? refL : refR;
   } else {
-    bool found = false;
+    T.cur = -1;
     while (T.sp > 0) {
       --T.sp;
       const float2 e = st.base[T.sp * st.stride];
       if (!(e.y > lim)) {
         T.cur = __float_as_int(e.x);
-        found = true;
         break;
       }
     }
-    T.active = found;
   }
 }
 
@@ -362,19 +453,19 @@ RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int
 template <bool SMEM>
 RT_DEV void test_parked(const SceneView &S, Trav &T, uint32_t ref, v3 o, v3 d) {
   test_triangle<SMEM>(S, ~(int)ref, o, d, T.best, T.best_rank);
-  T.lim = cull_limit(S, T.best.k);
+  T.lim = cull_limit(S, T);
 }
 
 // the whole walk by one thread (k_primary, k_trace_rays, verify mode); `parks` = kParkCap words of this thread
 template <bool SMEM, bool STATS>
 RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, uint32_t *parks, int pstride,
                             TraceCounters *cnt) {
-  if (!ray_is_fast(S, o, d)) return closest_hit_nodrop<SMEM>(S, o, d);
+  if (!ray_is_fast(S, o)) return closest_hit_nodrop<SMEM>(S, o, d);
   Trav T;
   int pn = 0;
   trav_begin<SMEM, STATS>(S, T, o, d, pn, parks, cnt);
-  while (T.active || pn > 0) {
-    if (pn > 0 && (!T.active || pn > kParkCap - 2)) {
+  while (trav_active(T) || pn > 0) {
+    if (pn > 0 && (!trav_active(T) || pn > kParkCap - 2)) {
       --pn;
       if (STATS) cnt->tri_tests++;
       test_parked<SMEM>(S, T, parks[pn * pstride], o, d);
@@ -382,7 +473,7 @@ RT_DEV Hit closest_hit_fast(const SceneView &S, v3 o, v3 d, LaneStack st, uint32
       trav_step<SMEM, STATS>(S, T, pn, parks, pstride, st, cnt);
     }
   }
-  if (T.best.tri >= 0 && !validate_hit(S, o, d, T.best.tri)) return closest_hit_nodrop<SMEM>(S, o, d);
+  if (T.best.tri >= 0 && !validate_winner(S, o, d, T.best.tri, T.best_rank)) return closest_hit_nodrop<SMEM>(S, o, d);
   return T.best;
 }
 

@@ -1,0 +1,372 @@
+// Validation and repacking of the reference-layout scene (FileManager.py / BVH.py buffers) for the
+// traversal kernels — host code only, OpenMP over triangles and over interior nodes.  The one serial stage is the
+// right-first walk of the tree, which fixes every leaf's rank in the reference's visiting order (MathLib.cl:252-280).
+#include "scene_repack.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/b200rt.h"
+
+namespace b200rt {
+
+namespace {
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+std::string fmt(const char *f, long long a = 0, long long b = 0, long long c = 0) {
+  char buf[256];
+  snprintf(buf, sizeof buf, f, a, b, c);
+  return buf;
+}
+
+float as_float(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+uint32_t as_u32(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
+// smallest value with only the upper 16 bits of a binary32 set that is >= x (x >= 0, finite)
+float bf16_up(double x) {
+  float f = (float)x;
+  if ((double)f < x) f = std::nextafterf(f, INFINITY);
+  uint32_t u = as_u32(f);
+  if (u & 0xffffu) u = (u + 0x10000u) & 0xffff0000u;
+  return as_float(u);
+}
+
+// The grid of one axis: decoded centre = base + fc * pitch, fc = 0.5 + q / 65536, q in [0, 32767].
+struct Axis {
+  float base, pitch;
+};
+
+// (q, hq) whose decoded box encloses [mn, mx] in real arithmetic
+void quantise(const Axis &g, float mn, float mx, uint32_t *q_out, float *hq_out) {
+  const long double base = g.base, pitch = g.pitch;
+  const long double mid = 0.5L * ((long double)mn + (long double)mx);
+  long double qf = ((mid - base) / pitch - 0.5L) * 65536.0L;
+  long long q = (long long)std::floor((double)qf + 0.5);
+  q = std::min<long long>(std::max<long long>(q, 0), 32767);
+  const long double fc = 0.5L + (long double)q / 65536.0L;
+  const long double c = base + fc * pitch;  // the product is exact (16 x 24 bits); the sum may round in the 64th bit
+  const long double slack = (std::fabs(base) + pitch) * 0x1p-58L;
+  const long double need = std::max(c - (long double)mn, (long double)mx - c) + slack;
+  float hq = bf16_up((double)(need / pitch) * (1.0 + 0x1p-40));
+  while ((long double)hq * pitch < need) hq = as_float(as_u32(hq) + 0x10000u);
+  *q_out = (uint32_t)q;
+  *hq_out = hq;
+}
+
+}  // namespace
+
+int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const int32_t *face, int64_t n_face,
+                 int64_t n_materials, const float *bvh, int64_t n_bvh, Repacked *out, std::string *err) {
+  Repacked &R = *out;
+  const int n_nodes = (int)(n_bvh / 9), n_tris = (int)(n_face / 10);
+  const int nvp = (int)(n_vp / 3), nvn = (int)(n_vn / 3), nm = (int)n_materials;
+  R.n_nodes9 = n_nodes;
+  R.n_tris = n_tris;
+  double t0 = now_ms();
+
+  // ---- triangles: validate indices, precompute edges exactly as MathLib.cl:129-130 rounds them ------------------
+  R.tris.resize((size_t)n_tris * 3);
+  R.normals.resize((size_t)n_tris);
+  R.tboxes.assign((size_t)n_tris * 2, Repacked::f4{0, 0, 0, 0});
+  R.tri_mat.resize((size_t)n_tris);
+  float cmax = 0.0f;
+  int first_bad = n_tris;   // first triangle with an out-of-range index
+  int nonfinite = 0;
+  const float unranked = as_float(0x7fffffffu);
+#pragma omp parallel for schedule(static) reduction(max : cmax) reduction(min : first_bad) reduction(| : nonfinite)
+  for (int t = 0; t < n_tris; ++t) {
+    const int32_t *f = face + 10 * (size_t)t;
+    bool ok = f[4] >= 0 && f[4] < nvn && f[0] >= 0 && f[0] < nm;
+    for (int j = 7; j < 10; ++j) ok = ok && f[j] >= 0 && f[j] < nvp;
+    if (!ok) {
+      if (t < first_bad) first_bad = t;
+      continue;
+    }
+    const float *a = vp + 3 * (size_t)f[7], *b = vp + 3 * (size_t)f[8], *c = vp + 3 * (size_t)f[9];
+    const float e1x = b[0] - a[0], e1y = b[1] - a[1], e1z = b[2] - a[2];
+    const float e2x = c[0] - a[0], e2y = c[1] - a[1], e2z = c[2] - a[2];
+    R.tris[3 * (size_t)t + 0] = Repacked::f4{a[0], a[1], a[2], e1x};
+    R.tris[3 * (size_t)t + 1] = Repacked::f4{e1y, e1z, e2x, e2y};
+    R.tris[3 * (size_t)t + 2] = Repacked::f4{e2z, as_float((uint32_t)f[0]), unranked, 0.0f};
+    const float *n0 = vn + 3 * (size_t)f[4];
+    R.normals[t] = Repacked::f4{n0[0], n0[1], n0[2], 0.0f};
+    R.tri_mat[t] = f[0];
+    for (int j = 7; j < 10; ++j)
+      for (int k = 0; k < 3; ++k) {
+        const float v = std::fabs(vp[3 * (size_t)f[j] + k]);
+        if (!std::isfinite(v)) nonfinite |= 1;
+        else if (v > cmax) cmax = v;
+      }
+  }
+  if (first_bad < n_tris) {
+    const int32_t *f = face + 10 * (size_t)first_bad;
+    for (int j = 7; j < 10; ++j)
+      if (f[j] < 0 || f[j] >= nvp) {
+        *err = fmt("triangle %lld: position index %lld out of range [0,%lld)", first_bad, f[j], nvp);
+        return B200RT_ERR_INVALID;
+      }
+    if (f[4] < 0 || f[4] >= nvn) {
+      *err = fmt("triangle %lld: normal index %lld out of range [0,%lld)", first_bad, f[4], nvn);
+      return B200RT_ERR_INVALID;
+    }
+    *err = fmt("triangle %lld: material %lld out of range [0,%lld)", first_bad, f[0], nm);
+    return B200RT_ERR_INVALID;
+  }
+  double t1 = now_ms();
+  R.ms_tris = t1 - t0;
+
+  // ---- nodes: validate, detect tree shape, rank leaves in the reference's visiting order -----------------------
+  std::vector<int> inner_id((size_t)n_nodes, -1);
+  std::vector<unsigned char> seen((size_t)n_nodes, 0);
+  bool canonical = true;
+  auto L = [&](int i) { return (int)bvh[9 * (size_t)i]; };
+  auto Rc = [&](int i) { return (int)bvh[9 * (size_t)i + 1]; };
+  auto T = [&](int i) { return (int)bvh[9 * (size_t)i + 8]; };
+  int depth = 0;
+  size_t max_stack = 1;
+  std::vector<int> preorder;
+  preorder.reserve((size_t)n_nodes);
+  {
+    // right-first pre-order walk == the order MathLib.cl:252-280 pops nodes when every box test passes
+    struct Item { int node, level; };
+    std::vector<Item> stack;
+    stack.push_back({0, 0});
+    int rank = 0;
+    while (!stack.empty()) {
+      const Item it = stack.back();
+      stack.pop_back();
+      const int cur = it.node;
+      if (cur < 0 || cur >= n_nodes) {
+        *err = fmt("BVH child index %lld out of range [0,%lld)", cur, n_nodes);
+        return B200RT_ERR_INVALID;
+      }
+      if (seen[cur]) {
+        *err = fmt("BVH node %lld is reachable twice: not a tree (the traversal would not terminate)", cur);
+        return B200RT_ERR_INVALID;
+      }
+      seen[cur] = 1;
+      preorder.push_back(cur);
+      const float *rec = bvh + 9 * (size_t)cur;
+      const int l = (int)rec[0], r = (int)rec[1], t = (int)rec[8];
+      if (t < -1 || t >= n_tris) {
+        *err = fmt("BVH node %lld: triangle %lld out of range [0,%lld)", cur, t, n_tris);
+        return B200RT_ERR_INVALID;
+      }
+      if (l < -1 || r < -1) {
+        *err = fmt("BVH node %lld: negative child index", cur);
+        return B200RT_ERR_INVALID;
+      }
+      const float *bx = rec + 2;
+      for (int k = 0; k < 6; ++k) {
+        const float v = std::fabs(bx[k]);
+        if (!std::isfinite(v)) nonfinite |= 1;
+        else if (v > cmax) cmax = v;
+      }
+      const bool leaf = (t != -1 && l == -1 && r == -1), inner = (t == -1 && l != -1 && r != -1);
+      if (!leaf && !inner) canonical = false;
+      // the fast traversal's "leaf passes => ancestors pass" argument needs min <= max and child boxes nested in
+      // their parent's (rt_trace.cuh); BVH.py guarantees both, anything else is walked in reference order
+      for (int k = 0; k < 3; ++k)
+        if (!(bx[k] <= bx[k + 3])) canonical = false;
+      for (int ch : {l, r})
+        if (ch >= 0 && ch < n_nodes) {
+          const float *cb = bvh + 9 * (size_t)ch + 2;
+          for (int k = 0; k < 3; ++k)
+            if (!(cb[k] >= bx[k] && cb[k + 3] <= bx[k + 3])) canonical = false;
+        }
+      if (t != -1) {
+        Repacked::f4 &t2 = R.tris[3 * (size_t)t + 2];
+        if (as_u32(t2.z) == 0x7fffffffu) {
+          t2.z = as_float((uint32_t)rank);
+          R.tboxes[2 * (size_t)t] = Repacked::f4{bx[0], bx[1], bx[2], 0.0f};
+          R.tboxes[2 * (size_t)t + 1] = Repacked::f4{bx[3], bx[4], bx[5], 0.0f};
+        } else {
+          canonical = false;  // a triangle held by two leaves: rank and leaf box would be ambiguous
+        }
+        ++rank;
+      }
+      if (it.level > depth) depth = it.level;
+      if (l != -1) stack.push_back({l, it.level + 1});
+      if (r != -1) stack.push_back({r, it.level + 1});
+      if (stack.size() > max_stack) max_stack = stack.size();
+    }
+  }
+  if (nonfinite) {
+    *err = "scene contains a non-finite coordinate (vertex or box plane)";
+    return B200RT_ERR_INVALID;
+  }
+  // leaves per sub-tree: children come after their parent in the pre-order, so the reverse order is bottom-up
+  R.leaf_count.assign((size_t)n_nodes, 0);
+  for (size_t q = preorder.size(); q-- > 0;) {
+    const int cur = preorder[q];
+    const float *rec = bvh + 9 * (size_t)cur;
+    const int l = (int)rec[0], r = (int)rec[1];
+    R.leaf_count[cur] = ((int)rec[8] != -1 ? 1 : 0) + (l != -1 ? R.leaf_count[l] : 0) + (r != -1 ? R.leaf_count[r] : 0);
+  }
+  R.depth = depth;
+  R.ref_stack_need = (int)max_stack;
+  if (R.ref_stack_need > kRefStackMax) canonical = false;  // closest_hit_nodrop's thread-local stack
+  // a pathologically deep tree would not leave room for the per-lane stacks in shared memory
+  if (lane_smem_bytes_host(depth + 2) > kLaneSmemMax) canonical = false;
+  double t2 = now_ms();
+  R.ms_walk = t2 - t1;
+
+  // ---- grid of the quantised node boxes ------------------------------------------------------------------
+  Axis grid[3];
+  {
+    double ext[3], ext_max = 0.0;
+    for (int k = 0; k < 3; ++k) {
+      ext[k] = std::max(0.0, (double)bvh[5 + k] - (double)bvh[2 + k]);
+      ext_max = std::max(ext_max, ext[k]);
+    }
+    if (ext_max == 0.0) ext_max = std::max((double)cmax, 1e-30) * 0x1p-12;
+    for (int k = 0; k < 3; ++k) {
+      const double e = std::max(ext[k], ext_max / 256.0);   // bounded anisotropy: a flat scene keeps a usable pitch
+      float pitch = (float)(e * (65536.0 / 32767.0) * (1.0 + 0x1p-20));
+      if (!(pitch > 0.0f) || !std::isfinite(pitch)) pitch = 1.0f;
+      float base = (float)((double)bvh[2 + k] - 0.5 * (double)pitch);
+      if ((double)base > (double)bvh[2 + k] - 0.5 * (double)pitch) base = std::nextafterf(base, -INFINITY);
+      if (!std::isfinite(base)) base = 0.0f;
+      grid[k] = Axis{base, pitch};
+      R.grid_base[k] = base;
+      R.grid_pitch[k] = pitch;
+      const float hi = std::fabs(base + pitch) * (1.0f + 0x1p-20f), lo = std::fabs(base);
+      cmax = std::max(cmax, std::max(hi, lo));
+      uint32_t q;
+      float hq;
+      quantise(grid[k], bvh[2 + k], bvh[5 + k], &q, &hq);
+      R.root_fc[k] = 0.5f + (float)q / 65536.0f;
+      R.root_hq[k] = hq;
+    }
+    const float dx = bvh[5] - bvh[2], dy = bvh[6] - bvh[3], dz = bvh[7] - bvh[4];
+    R.cull_abs = 1e-3f * std::sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  R.cmax = cmax;
+  // range the conservative slab test's error margin is proven for (rt_trace.cuh); outside it every ray takes
+  // closest_hit_nodrop
+  R.fast_ok = (cmax <= 1.099511627776e12f /* 2^40 */ && cmax >= 9.5367431640625e-07f /* 2^-20 */) ? 1 : 0;
+
+  // ---- repack interior nodes into the 32-byte two-child records ---------------------------------------------------
+  // Order: a node's interior children are adjacent, and a pair is followed by the sub-tree of its first member
+  // (pre-order over sibling pairs), so that the 128-byte line that holds a node usually holds the next node of a
+  // descent as well — what matters once the tree no longer fits the caches (BASELINE config 5).
+  R.nodes.clear();
+  R.n_inner = 0;
+  R.root_ref = 0;
+  R.canonical = canonical;
+  if (canonical) {
+    if (T(0) != -1) {
+      R.root_ref = ~T(0);
+    } else {
+      std::vector<int> order;
+      order.reserve((size_t)n_nodes / 2 + 1);
+      order.push_back(0);
+      inner_id[0] = 0;
+      if (const char *e = getenv("B200RT_NODE_ORDER"); e && e[0] == 'b') {  // experiment: breadth-first
+        for (size_t q = 0; q < order.size(); ++q) {
+          const int cur = order[q];
+          const int ch[2] = {L(cur), Rc(cur)};
+          for (int k = 0; k < 2; ++k)
+            if (T(ch[k]) == -1) {
+              inner_id[ch[k]] = (int)order.size();
+              order.push_back(ch[k]);
+            }
+        }
+      } else {
+        std::vector<int> todo;
+        todo.push_back(0);
+        while (!todo.empty()) {
+          const int cur = todo.back();
+          todo.pop_back();
+          const int ch[2] = {L(cur), Rc(cur)};
+          for (int k = 0; k < 2; ++k)
+            if (T(ch[k]) == -1) {
+              inner_id[ch[k]] = (int)order.size();
+              order.push_back(ch[k]);
+            }
+          for (int k = 1; k >= 0; --k)
+            if (T(ch[k]) == -1) todo.push_back(ch[k]);
+        }
+      }
+      const int n_inner = (int)order.size();
+      R.n_inner = n_inner;
+      // small scenes are staged in shared memory with 48-byte node spacing (SceneView::node_f4)
+      const int nf4 = ((size_t)n_inner * 48 + (size_t)n_tris * 48 <= kSmemSceneMax) ? 3 : 2;
+      R.node_f4 = nf4;
+      R.nodes.assign((size_t)n_inner * nf4, Repacked::u4{0, 0, 0, 0});
+#pragma omp parallel for schedule(static)
+      for (int q = 0; q < n_inner; ++q) {
+        const int cur = order[q];
+        const int l = L(cur), r = Rc(cur);
+        const float *bl = bvh + 9 * (size_t)l, *br = bvh + 9 * (size_t)r;
+        // interior refs are 16-byte offsets into the node array (index x 16-byte units per node)
+        const int32_t refl = T(l) != -1 ? ~T(l) : (int32_t)(inner_id[l] * nf4);
+        const int32_t refr = T(r) != -1 ? ~T(r) : (int32_t)(inner_id[r] * nf4);
+        uint32_t ql[3], qr[3];
+        float hl[3], hr[3];
+        for (int k = 0; k < 3; ++k) {
+          quantise(grid[k], bl[2 + k], bl[5 + k], &ql[k], &hl[k]);
+          quantise(grid[k], br[2 + k], br[5 + k], &qr[k], &hr[k]);
+        }
+        auto hi16 = [](float f) { return as_u32(f) & 0xffff0000u; };
+        auto lo16 = [](float f) { return as_u32(f) >> 16; };
+        Repacked::u4 a, b;
+        a.x = (ql[0] << 16) | ql[1];
+        a.y = (ql[2] << 16) | qr[0];
+        a.z = (qr[1] << 16) | qr[2];
+        a.w = hi16(hl[0]) | lo16(hl[1]);
+        b.x = hi16(hl[2]) | lo16(hr[0]);
+        b.y = hi16(hr[1]) | lo16(hr[2]);
+        b.z = (uint32_t)refl;
+        b.w = (uint32_t)refr;
+        R.nodes[(size_t)nf4 * q + 0] = a;
+        R.nodes[(size_t)nf4 * q + 1] = b;
+      }
+    }
+  }
+  R.ms_nodes = now_ms() - t2;
+  return 0;
+}
+
+}  // namespace b200rt
+
+extern "C" int b200rt_repack_probe(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const int32_t *face,
+                                   int64_t n_face, int64_t n_materials, const float *bvh, int64_t n_bvh,
+                                   uint32_t *nodes_out, int64_t n_nodes_out, float *info) {
+  if (!vp || !vn || !face || !bvh || !info || n_vp <= 0 || n_vp % 3 || n_vn <= 0 || n_vn % 3 || n_face <= 0 || n_face % 10 ||
+      n_bvh <= 0 || n_bvh % 9 || n_materials <= 0)
+    return B200RT_ERR_INVALID;
+  b200rt::Repacked R;
+  std::string msg;
+  int rc = b200rt::repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_materials, bvh, n_bvh, &R, &msg);
+  if (rc) return rc;
+  info[0] = (float)R.n_inner; info[1] = (float)R.node_f4; info[2] = (float)R.depth; info[3] = (float)R.ref_stack_need;
+  info[4] = R.canonical ? 1.0f : 0.0f; info[5] = (float)R.fast_ok; info[6] = R.cmax; info[7] = R.cull_abs;
+  for (int k = 0; k < 3; ++k) {
+    info[8 + k] = R.grid_base[k]; info[11 + k] = R.grid_pitch[k]; info[14 + k] = R.root_fc[k]; info[17 + k] = R.root_hq[k];
+  }
+  if (nodes_out) {
+    if (n_nodes_out < (int64_t)R.n_inner * 8) return B200RT_ERR_INVALID;
+    for (int q = 0; q < R.n_inner; ++q) {
+      const b200rt::Repacked::u4 &a = R.nodes[(size_t)R.node_f4 * q], &b = R.nodes[(size_t)R.node_f4 * q + 1];
+      uint32_t *o = nodes_out + 8 * (size_t)q;
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,40 @@
+// Host-side validation and repacking of the reference-layout scene buffers into the layouts
+// rt_trace.cuh consumes.  No CUDA calls: b200rt_set_scene uploads the result and commits it to the context only
+// after every copy has succeeded.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace b200rt {
+
+struct Repacked {
+  struct f4 { float x, y, z, w; };
+  struct u4 { uint32_t x, y, z, w; };
+  std::vector<u4> nodes;        // node_f4 x 16 bytes per interior node (rt_trace.cuh "repacked scene")
+  std::vector<f4> tris, normals, tboxes;
+  std::vector<int32_t> tri_mat;
+  std::vector<int32_t> leaf_count;  // per node of the as-is array: leaves in its sub-tree (validate_chain, rt_trace.cuh)
+  int n_nodes9 = 0, n_inner = 0, n_tris = 0;
+  int node_f4 = 2;              // 2 in global memory, 3 when nodes + triangles fit the shared-memory staging area
+  int depth = 0, ref_stack_need = 0;
+  bool canonical = true;        // strict two-child tree with nested boxes: the fast traversal applies
+  int root_ref = 0;
+  float grid_base[3] = {0, 0, 0}, grid_pitch[3] = {1, 1, 1}, root_fc[3] = {0.5f, 0.5f, 0.5f}, root_hq[3] = {0, 0, 0};
+  float cull_abs = 0.0f, cmax = 0.0f;
+  int fast_ok = 0;
+  double ms_tris = 0, ms_walk = 0, ms_nodes = 0;  // host time of the three stages
+};
+
+constexpr size_t kSmemSceneMax = 48 * 1024;  // repacked nodes + triangles up to this size are staged in shared memory
+constexpr int kRefStackMax = 64;             // thread-local stack of the exact walk (rt_trace.cuh kRefStack)
+constexpr size_t kLaneSmemMax = 96 * 1024;   // room for the per-lane shared-memory stacks of one CTA
+
+// bytes of per-lane traversal state in shared memory for a stack of `stack_depth` entries (rt_kernels.cuh lays it out)
+size_t lane_smem_bytes_host(int stack_depth);
+
+// Returns 0, or a negative b200rt_status with *err describing the first offending element.
+int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const int32_t *face, int64_t n_face,
+                 int64_t n_materials, const float *bvh, int64_t n_bvh, Repacked *out, std::string *err);
+
+}  // namespace b200rt

@@ -80,6 +80,12 @@ typedef struct {
   int32_t revalidated;    /* rays whose fast-traversal winner failed the exact leaf-box test and were re-traced exactly */
   float shade_kernel_ms;  /* only with time_kernels: summed device time of the k_shade launches */
   float trace_kernel_ms;  /* only with time_kernels: summed device time of the k_trace launches */
+  float repack_ms;        /* host time b200rt_set_scene spent validating and repacking the last scene (inside upload_ms) */
+  int32_t ref_stack_need; /* stack entries the reference's own walk needs on this tree; above 20 its capped stack drops
+                             pushes (stack.cl:21-26) and only B200RT_TRAVERSAL_REFERENCE reproduces that */
+  int32_t exact_walks;    /* wavefront rays with a zero / denormal / huge direction component, which skip the conservative
+                             traversal and are walked exactly by the shading kernel */
+  int32_t reserved0;
 } b200rt_stats;
 
 void b200rt_default_opts(b200rt_opts *opts);
@@ -183,6 +189,16 @@ int b200rt_ipc_close(b200rt_ctx *ctx, void *d_ptr);
  * input on which BVH.py itself does not terminate (every centroid of some node on one side of its mean). */
 int b200rt_build_bvh(const float *vertex_p, int64_t n_vertex_p, const int32_t *face_data, int64_t n_face_data,
                      float *bvh_out, int64_t n_bvh_out, int32_t *depth_out);
+
+/* Host-only view of what b200rt_set_scene uploads (no context, no GPU): validates the buffers exactly as
+ * b200rt_set_scene does and writes the repacked interior-node records (8 x uint32 each, csrc/rt_trace.cuh "repacked
+ * scene") to nodes_out (capacity in uint32 words; may be NULL to query).  info_out (20 floats): [0] interior nodes,
+ * [1] 16-byte units per node, [2] tree depth, [3] stack entries the reference-order walk needs, [4] canonical (fast
+ * traversal applies), [5] fast_ok, [6] cmax, [7] cull_abs, [8..10] grid base, [11..13] grid pitch, [14..16] root fc,
+ * [17..19] root hq.  Lets the CPU test-suite check that every quantised box encloses the exact one. */
+int b200rt_repack_probe(const float *vertex_p, int64_t n_vertex_p, const float *vertex_n, int64_t n_vertex_n,
+                        const int32_t *face_data, int64_t n_face_data, int64_t n_materials, const float *bvh,
+                        int64_t n_bvh, uint32_t *nodes_out, int64_t n_nodes_out, float *info_out);
 
 const char *b200rt_version(void);
 

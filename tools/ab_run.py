@@ -10,6 +10,10 @@ sys.path.insert(0, ROOT)
 from ensem3a_openclraytracer_b200 import _capi  # noqa: E402
 
 _capi.LIB_PATH = os.path.abspath(sys.argv[1])
+if os.environ.get("AB_OLD_ABI"):   # a library built from an older commit: bind only what it exports
+    import ctypes
+    _probe = ctypes.CDLL(_capi.LIB_PATH)
+    _capi.SYMBOLS = [s for s in _capi.SYMBOLS if hasattr(_probe, s)]
 import ensem3a_openclraytracer_b200 as rt  # noqa: E402
 from tests import fixtures  # noqa: E402
 
@@ -31,14 +35,20 @@ def main():
                 best = st
         split = ""
         try:
+            ctx.render(cam, env, w, h, min(spp, 2), 4, opts=rt.make_opts(rng_mode=1, traversal=0, seed=0, collect_stats=True))
+            st = ctx.stats()
+            split = f" | box/ray {st['box_tests'] / st['rays']:.2f} tri/ray {st['tri_tests'] / st['rays']:.2f}"
+        except Exception as e:  # noqa: BLE001
+            split = f" | stats failed: {e}"
+        try:
             ctx.render(cam, env, w, h, spp, 4, opts=rt.make_opts(rng_mode=1, traversal=0, seed=0, time_kernels=True))
             st = ctx.stats()
-            split = f" | k_trace {st['trace_kernel_ms']:.2f} k_shade {st['shade_kernel_ms']:.2f} ms"
+            split += f" | k_trace {st['trace_kernel_ms']:.2f} k_shade {st['shade_kernel_ms']:.2f} ms"
         except TypeError:
             pass
         print(f"{os.path.basename(sys.argv[1])} {name} {w}x{h} spp{spp}: rays {best['rays']} total {best['total_ms']:.2f} ms "
               f"{best['rays'] / best['total_ms'] / 1e3:.1f} Mrays/s mean {float(out.mean()):.6f} primary {best['primary_ms']:.2f} ms "
-              f"launches {best['kernel_launches']} reval {best.get('revalidated')}{split}", flush=True)
+              f"launches {best['kernel_launches']} reval {best.get('revalidated')} exact {best.get('exact_walks')}{split}", flush=True)
 
 
 if __name__ == "__main__":
