@@ -931,7 +931,7 @@ int b200rt_get_stats(const b200rt_ctx *c, b200rt_stats *s) {
 
 int b200rt_math_probe(b200rt_ctx *c, int fn, const float *a, const float *b, int64_t n, float *out) {
   if (!c) return B200RT_ERR_INVALID;
-  if (!a || !out || n <= 0 || fn < 0 || fn > 14) return fail(c, B200RT_ERR_INVALID, "bad math_probe arguments");
+  if (!a || !out || n <= 0 || fn < 0 || fn > 16) return fail(c, B200RT_ERR_INVALID, "bad math_probe arguments");
   CU(cudaSetDevice(c->device));
   size_t bytes = (size_t)n * sizeof(float);
   if (ensure(c, c->d_tmp_a, bytes)) return B200RT_ERR_CUDA;

@@ -660,6 +660,9 @@ __global__ void k_math_probe(int fn, const float *a, const float *b, long long n
     case 12: r = (float)texel_coord(cr_atan2(x, y), 0.1591f, 8192); break;    // correctly rounded angle only
     case 13: r = (float)ibl_texel_v(x, 4096); break;
     case 14: r = (float)texel_coord(cr_asin(x), 0.3183f, 4096); break;
+    case 15: { const float a = atan2f(x, y), del = fabsf(a) * 4.76837158203125e-07f;   // 1 = the column needs the exact angle (600 wide)
+               r = texel_coord(a - del, 0.1591f, 600) != texel_coord(a + del, 0.1591f, 600) ? 1.0f : 0.0f; break; }
+    case 16: r = atan2f(x, y); break;
   }
   out[i] = r;
 }

@@ -34,10 +34,6 @@
 #pragma once
 #include "rt_math.cuh"
 
-#ifndef B200RT_PREFETCH
-#define B200RT_PREFETCH 0
-#endif
-
 namespace b200rt {
 
 // ---- repacked scene -------------------------------------------------------------------------------
@@ -117,14 +113,23 @@ RT_DEV float hq_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 RT_DEV float hq_lo(uint32_t w) { return __uint_as_float(w << 16); }
 
 // ---- exact slab test, MathLib.cl:169-188 --------------------------------------------------------------
+// x / d, IEEE round-to-nearest.  The hardware division routine sends a zero numerator to its out-of-line slow path
+// (~40 instructions behind a call), and zero numerators are the common case here: a ray leaving a wall at z = -1 and
+// tested against a box that starts at z = -1.  (+-0) / d is the zero with the sign of x XOR d for every d other than
+// 0 and NaN, which this returns directly.
+RT_DEV float div_exact(float x, float d) {
+  if (x == 0.0f && d != 0.0f && d == d) return __uint_as_float((__float_as_uint(x) ^ __float_as_uint(d)) & 0x80000000u);
+  return __fdiv_rn(x, d);
+}
+
 RT_DEV bool slab_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float *tmin,
                        float *tmax) {
-  float a = __fdiv_rn(mnx - o.x, d.x), b = __fdiv_rn(mxx - o.x, d.x);
+  float a = div_exact(mnx - o.x, d.x), b = div_exact(mxx - o.x, d.x);
   float lo = fminf(a, b), hi = fmaxf(a, b);
-  a = __fdiv_rn(mny - o.y, d.y); b = __fdiv_rn(mxy - o.y, d.y);
+  a = div_exact(mny - o.y, d.y); b = div_exact(mxy - o.y, d.y);
   lo = fmaxf(lo, fminf(a, b));
   hi = fminf(hi, fmaxf(a, b));
-  a = __fdiv_rn(mnz - o.z, d.z); b = __fdiv_rn(mxz - o.z, d.z);
+  a = div_exact(mnz - o.z, d.z); b = div_exact(mxz - o.z, d.z);
   lo = fmaxf(lo, fminf(a, b));
   hi = fminf(hi, fmaxf(a, b));
   *tmin = lo;
@@ -403,17 +408,6 @@ RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int
   uint4 wa, wb;
   ld_node<SMEM>(S.nodes + T.cur, wa, wb);
   const int refL = (int)wb.z, refR = (int)wb.w;
-#if B200RT_PREFETCH
-  if (!SMEM) {  // experiment: start fetching both children's records while this node's boxes are tested
-#if B200RT_PREFETCH == 1
-#define B200RT_PF "prefetch.global.L1 [%0];"
-#else
-#define B200RT_PF "prefetch.global.L2 [%0];"
-#endif
-    if (refL >= 0) asm volatile(B200RT_PF ::"l"(S.nodes + refL));
-    if (refR >= 0) asm volatile(B200RT_PF ::"l"(S.nodes + refR));
-  }
-#endif
   float loL, hiL, loR, hiR;
   if (STATS) cnt->box_tests += 2;
   slab_cons(T.Q, fc_hi(wa.x), fc_lo(wa.x), fc_hi(wa.y), hq_hi(wa.w), hq_lo(wa.w), hq_hi(wb.x), &loL, &hiL);
