@@ -16,8 +16,18 @@ Differences a caller can observe (all documented in INTEGRATION.md):
   * non-square frames: width = int(cam[6]), height = imgDim // width, exactly what the reference
     kernel computes for such a launch (Raytracing.cl:21-29);
   * extra behaviour is opt-in through attributes (`rng_mode`, `traversal`, `seed`, ...) that the
-    reference's callers never touch, so the default is the reference's result.
+    reference's callers never touch, so the default is the reference's result — including on trees whose
+    walk needs more than the reference's 20 stack entries, where its stack silently drops pushes
+    (stack.cl:21-26): for such a tree the default switches to the reference-order walk with that cap (slow,
+    but the reference's image) and warns once; `deep_trees = "nodrop"` keeps the fast traversal, which visits
+    everything (the geometrically correct image, not the reference's);
+  * `cuda_devices=[0, 1, ...]` renders every frame on several GPUs of the box through the same call
+    (b200rt_multi_*): bit-identical with the reference generator, equal up to the order of the float additions
+    with `rng_mode = RNG_PHILOX`.
 """
+import os
+import warnings
+
 import numpy as np
 
 from . import _capi
@@ -25,19 +35,29 @@ from . import _capi
 
 class KernelLauncher(object):
 
-    def __init__(self, context=None, platform=None, device=None, queue=None, cuda_device=0):
+    def __init__(self, context=None, platform=None, device=None, queue=None, cuda_device=0, cuda_devices=None):
         self.platform = platform
         self.device = device
         self.context = context
         self.queue = queue
-        self._ctx = _capi.Context(cuda_device)
-        # opt-in knobs; defaults reproduce the reference
+        if cuda_devices is None and os.environ.get("B200RT_CUDA_DEVICES"):
+            # main.py:28 constructs the launcher with the four OpenCL objects only; a deployment that wants several
+            # GPUs behind the unchanged driver names them here, e.g. B200RT_CUDA_DEVICES=0,1,2,3,4,5,6,7
+            cuda_devices = [int(x) for x in os.environ["B200RT_CUDA_DEVICES"].split(",") if x.strip() != ""]
+        if cuda_devices is not None and len(cuda_devices) > 1:
+            self._ctx = _capi.MultiContext(cuda_devices)
+        else:
+            self._ctx = _capi.Context(cuda_devices[0] if cuda_devices else cuda_device)
+        # opt-in knobs; the defaults reproduce the reference's image
         self.rng_mode = _capi.RNG_REFERENCE
         self.traversal = _capi.TRAVERSAL_FAST
         self.seed = 0
-        self.stack_cap = 20
+        self.stack_cap = 20          # the reference's stack capacity (MathLib.cl:248); used by the reference-order walk
+        self.deep_trees = "reference"  # "reference": trees needing > stack_cap entries are walked like the reference
+        #                                 walks them (drops included); "nodrop": keep the fast, complete traversal
         self.collect_stats = False
         self.last_stats = None
+        self._warned_deep = False
 
     # reference KernelLauncher.py:33
     def launch_Raytracing(self, h_img_out, h_vertex_p, h_vertex_n, h_vertex_uv, h_face_data, h_material_data,
@@ -64,7 +84,17 @@ class KernelLauncher(object):
         else:
             self._ctx.set_ibl(np.asarray(h_IBL))
 
-        opts = _capi.make_opts(rng_mode=self.rng_mode, traversal=self.traversal, stack_cap=self.stack_cap,
+        traversal = self.traversal
+        need = self._ctx.stats()["ref_stack_need"]
+        if traversal == _capi.TRAVERSAL_FAST and need > self.stack_cap and self.deep_trees == "reference":
+            traversal = _capi.TRAVERSAL_REFERENCE
+            if not self._warned_deep:
+                warnings.warn(f"this BVH needs {need} traversal-stack entries; the reference's {self.stack_cap}-entry stack "
+                              "drops pushes on it (stack.cl:21-26).  Rendering with the reference-order walk to reproduce its "
+                              "image; set launcher.deep_trees = 'nodrop' for the fast traversal that visits everything.",
+                              RuntimeWarning, stacklevel=2)
+                self._warned_deep = True
+        opts = _capi.make_opts(rng_mode=self.rng_mode, traversal=traversal, stack_cap=self.stack_cap,
                                seed=self.seed, collect_stats=self.collect_stats)
         out = h_img_out.reshape(-1)[:imgDim * 3]
         self._ctx.render(cam[:10], h_envData, width, height, int(spp), int(maxBounce), out=out, opts=opts)

@@ -50,7 +50,10 @@ SYMBOLS = [
     "b200rt_reduce_finalize_device", "b200rt_sync", "b200rt_set_stream", "b200rt_invalidate", "b200rt_primary_hits", "b200rt_trace_rays",
     "b200rt_img_processing", "b200rt_get_stats", "b200rt_math_probe", "b200rt_philox_probe", "b200rt_alloc",
     "b200rt_free", "b200rt_ipc_export",
-    "b200rt_ipc_open", "b200rt_ipc_close", "b200rt_build_bvh", "b200rt_repack_probe", "b200rt_version",
+    "b200rt_ipc_open", "b200rt_ipc_close", "b200rt_build_bvh", "b200rt_repack_probe", "b200rt_version", "b200rt_device_count",
+    "b200rt_multi_create", "b200rt_multi_destroy", "b200rt_multi_last_error", "b200rt_multi_device_count",
+    "b200rt_multi_context", "b200rt_multi_set_scene", "b200rt_multi_set_ibl", "b200rt_multi_invalidate",
+    "b200rt_multi_render", "b200rt_multi_get_stats",
 ]
 
 _lib = None
@@ -105,9 +108,24 @@ def load_library():
     lib.b200rt_build_bvh.argtypes = [vp, i64, vp, i64, vp, i64, ctypes.POINTER(ctypes.c_int32)]
     if "b200rt_repack_probe" in SYMBOLS:
         lib.b200rt_repack_probe.argtypes = [vp, i64, vp, i64, vp, i64, i64, vp, i64, vp, i64, vp]
+    if "b200rt_multi_create" in SYMBOLS:
+        lib.b200rt_multi_create.argtypes = [ctypes.POINTER(ctypes.c_int), i32, ctypes.POINTER(vp)]
+        lib.b200rt_multi_destroy.restype = None
+        lib.b200rt_multi_destroy.argtypes = [vp]
+        lib.b200rt_multi_last_error.restype = ctypes.c_char_p
+        lib.b200rt_multi_last_error.argtypes = [vp]
+        lib.b200rt_multi_device_count.argtypes = [vp]
+        lib.b200rt_multi_context.restype = vp
+        lib.b200rt_multi_context.argtypes = [vp, i32]
+        lib.b200rt_multi_set_scene.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64]
+        lib.b200rt_multi_set_ibl.argtypes = [vp, vp, i32, i32]
+        lib.b200rt_multi_invalidate.argtypes = [vp]
+        lib.b200rt_multi_render.argtypes = [vp, vp, vp, i32, i32, i32, i32, ctypes.POINTER(Opts), vp]
+        lib.b200rt_multi_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("b200rt_version", "b200rt_last_error", "b200rt_default_opts", "b200rt_destroy"):
+        if name not in ("b200rt_version", "b200rt_last_error", "b200rt_default_opts", "b200rt_destroy",
+                        "b200rt_multi_destroy", "b200rt_multi_last_error", "b200rt_multi_context"):
             fn.restype = ctypes.c_int
     _lib = lib
     return lib
@@ -153,11 +171,17 @@ def build_bvh(face_data, vertex_p, return_depth=False):
     return (out, depth.value) if return_depth else out
 
 
+def device_count():
+    """CUDA devices visible to the process."""
+    lib = load_library()
+    return int(lib.b200rt_device_count()) if hasattr(lib, "b200rt_device_count") else 0
+
+
 def repack_probe(vertex_p, vertex_n, face_data, n_materials, bvh):
     """(nodes[n_inner, 8] uint32, info dict) — the interior-node records b200rt_set_scene would upload (host only)."""
     lib = load_library()
     vp_, vn_, face, bvh_ = _f32(vertex_p), _f32(vertex_n), _i32(face_data), _f32(bvh)
-    info = np.zeros(20, np.float32)
+    info = np.zeros(24, np.float32)
     rc = lib.b200rt_repack_probe(_ptr(vp_), vp_.size, _ptr(vn_), vn_.size, _ptr(face), face.size, int(n_materials),
                                  _ptr(bvh_), bvh_.size, None, 0, _ptr(info))
     if rc != 0:
@@ -170,15 +194,20 @@ def repack_probe(vertex_p, vertex_n, face_data, n_materials, bvh):
     d = dict(n_inner=int(info[0]), node_f4=int(info[1]), depth=int(info[2]), ref_stack_need=int(info[3]),
              canonical=bool(info[4]), fast_ok=bool(info[5]), cmax=float(info[6]), cull_abs=float(info[7]),
              grid_base=info[8:11].copy(), grid_pitch=info[11:14].copy(), root_fc=info[14:17].copy(),
-             root_hq=info[17:20].copy())
+             root_hq=info[17:20].copy(), ms_tris=float(info[20]), ms_walk=float(info[21]), ms_nodes=float(info[22]))
     return nodes, d
 
 
 class Context:
     """One GPU.  Thin, 1:1 over the C ABI; numpy in, numpy out."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _borrowed=None):
         self._lib = load_library()
+        self._owned = _borrowed is None
+        if _borrowed is not None:            # a context lent by a MultiContext (b200rt_multi_context)
+            self._h = ctypes.c_void_p(_borrowed)
+            self.device = int(device)
+            return
         h = ctypes.c_void_p()
         rc = self._lib.b200rt_create(int(device), ctypes.byref(h))
         if rc != 0:
@@ -188,7 +217,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.b200rt_destroy(self._h)
+            if self._owned:
+                self._lib.b200rt_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -359,3 +389,87 @@ class Context:
 
     def ipc_close(self, d_ptr):
         self._check(self._lib.b200rt_ipc_close(self._h, ctypes.c_void_p(int(d_ptr))), "b200rt_ipc_close")
+
+
+class MultiContext:
+    """Several GPUs of one box behind one handle (b200rt_multi_*): same set_scene / set_ibl / render / stats surface as
+    Context, the frame divided among the GPUs inside the library.  `contexts[i]` are the per-GPU contexts (lent)."""
+
+    def __init__(self, devices):
+        self._lib = load_library()
+        devs = [int(d) for d in devices]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        h = ctypes.c_void_p()
+        rc = self._lib.b200rt_multi_create(arr, len(devs), ctypes.byref(h))
+        if rc != 0:
+            raise B200RTError(f"b200rt_multi_create({devs}) failed ({rc}): {self._lib.b200rt_multi_last_error(None).decode()}")
+        self._h = h
+        self.devices = devs
+        self.device = devs[0]
+        self.contexts = [Context(d, _borrowed=self._lib.b200rt_multi_context(h, i)) for i, d in enumerate(devs)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for c in self.contexts:
+                c.close()
+            self._lib.b200rt_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise B200RTError(f"{what} failed ({rc}): {self._lib.b200rt_multi_last_error(self._h).decode()}")
+
+    def set_scene(self, vertex_p, vertex_n, vertex_uv, face_data, material_data, light_data, bvh):
+        vp_, vn_, vuv_ = _f32(vertex_p), _f32(vertex_n), _f32(vertex_uv)
+        face, mat, bvh_ = _i32(face_data), _f32(material_data), _f32(bvh)
+        light = _i32(light_data) if light_data is not None and len(light_data) else None
+        self._check(self._lib.b200rt_multi_set_scene(self._h, _ptr(vp_), vp_.size, _ptr(vn_), vn_.size, _ptr(vuv_), vuv_.size,
+                                                     _ptr(face), face.size, _ptr(mat), mat.size, _ptr(light),
+                                                     0 if light is None else light.size, _ptr(bvh_), bvh_.size),
+                    "b200rt_multi_set_scene")
+
+    def set_ibl(self, rgba, width=None, height=None):
+        if isinstance(rgba, (bytes, bytearray, memoryview)):
+            arr = np.frombuffer(rgba, dtype=np.uint8)
+        else:
+            arr = np.ascontiguousarray(rgba, dtype=np.uint8)
+            if width is None:
+                height, width = arr.shape[0], arr.shape[1]
+            arr = arr.reshape(-1)
+        if arr.size != int(width) * int(height) * 4:
+            raise B200RTError(f"environment map: {arr.size} bytes for {width}x{height} RGBA")
+        self._check(self._lib.b200rt_multi_set_ibl(self._h, _ptr(arr), int(width), int(height)), "b200rt_multi_set_ibl")
+
+    def invalidate(self):
+        self._check(self._lib.b200rt_multi_invalidate(self._h), "b200rt_multi_invalidate")
+
+    def render(self, cam, env, width, height, spp, max_bounce, out=None, opts=None):
+        cam_, env_ = _f32(cam), _f32(env)
+        if cam_.size != 10 or env_.size != 5:
+            raise B200RTError("cam must hold 10 floats and envData 5 (main.py:59-61,72-73)")
+        n = int(width) * int(height) * 3
+        if out is None:
+            out = np.zeros(n, dtype=np.float32)
+        if out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or out.size != n:
+            raise B200RTError(f"out must be a C-contiguous float32 array of {n} elements")
+        o = opts if opts is not None else make_opts()
+        self._check(self._lib.b200rt_multi_render(self._h, _ptr(cam_), _ptr(env_), int(width), int(height), int(spp),
+                                                  int(max_bounce), ctypes.byref(o), _ptr(out)), "b200rt_multi_render")
+        return out
+
+    def stats(self):
+        s = Stats()
+        self._check(self._lib.b200rt_multi_get_stats(self._h, ctypes.byref(s)), "b200rt_multi_get_stats")
+        return s.as_dict()
+
+    def img_processing(self, src, dst, n, global_size=None):
+        return self.contexts[0].img_processing(src, dst, n, global_size)
+
+    def primary_hits(self, cam, width, height, opts=None):
+        return self.contexts[0].primary_hits(cam, width, height, opts)

@@ -188,6 +188,8 @@ size_t smem_bytes(const b200rt_ctx *c, bool smem_scene) {
   return lane_smem_bytes(stack_entries(c)) + (smem_scene ? scene_smem_bytes(c) : 0);
 }
 
+int effective_stack_cap(const b200rt_ctx *c, const b200rt_opts &o);
+
 void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float *d_out, KernelArgs *A) {
   A->F = F;
   SceneView &S = A->S;
@@ -209,8 +211,7 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   }
   S.cull_abs = c->cull_abs;
   S.cmax = c->cmax;
-  int cap = o.stack_cap <= 0 ? 20 : (o.stack_cap > 64 ? 64 : o.stack_cap);
-  S.stack_cap = cap;
+  S.stack_cap = effective_stack_cap(c, o);
   S.fast_ok = c->fast_ok;
   A->ibl = c->ibl_tex;
   A->prim_dirk = static_cast<float4 *>(c->d_prim_dirk.p);
@@ -237,9 +238,17 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   A->validate = 0;
 }
 
+// The fast path needs a strict two-child tree with nested boxes; any other tree is walked in reference order.  When
+// the caller asked for FAST (a walk that never drops a push) the substitute keeps that promise as far as its
+// thread-local stack reaches: it runs with the largest cap instead of the reference's 20.
 int effective_traversal(const b200rt_ctx *c, const b200rt_opts &o) {
-  if (!c->canonical) return B200RT_TRAVERSAL_REFERENCE;  // the fast path needs a strict two-child tree
+  if (!c->canonical) return B200RT_TRAVERSAL_REFERENCE;
   return o.traversal;
+}
+
+int effective_stack_cap(const b200rt_ctx *c, const b200rt_opts &o) {
+  if (!c->canonical && o.traversal == B200RT_TRAVERSAL_FAST) return kRefStack;
+  return o.stack_cap <= 0 ? 20 : (o.stack_cap > kRefStack ? kRefStack : o.stack_cap);
 }
 
 template <typename K>
@@ -484,7 +493,16 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
 // ================================================================================================
 extern "C" {
 
-const char *b200rt_version(void) { return "b200rt 0.1 (sm_100a)"; }
+const char *b200rt_version(void) { return "b200rt 0.2 (sm_100a)"; }
+
+int b200rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
 
 void b200rt_default_opts(b200rt_opts *o) {
   memset(o, 0, sizeof *o);
@@ -583,53 +601,57 @@ int b200rt_set_materials(b200rt_ctx *c, const float *mat, int64_t n_mat) {
   return 0;
 }
 
-int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const float *vuv,
-                     int64_t n_vuv, const int32_t *face, int64_t n_face, const float *mat, int64_t n_mat,
-                     const int32_t *light, int64_t n_light, const float *bvh, int64_t n_bvh) {
-  (void)vuv; (void)n_vuv; (void)light; (void)n_light;  // fetched / passed but never used by the kernel (MathLib.cl:217, Raytracing.cl:163)
-  if (!c) return B200RT_ERR_INVALID;
-  auto t0 = std::chrono::steady_clock::now();
-  if (!vp || !vn || !face || !mat || !bvh) return fail(c, B200RT_ERR_INVALID, "NULL scene buffer");
-  if (n_vp <= 0 || n_vp % 3) return fail(c, B200RT_ERR_INVALID, "vertex_p length %lld is not a positive multiple of 3", (long long)n_vp);
-  if (n_vn <= 0 || n_vn % 3) return fail(c, B200RT_ERR_INVALID, "vertex_n length %lld is not a positive multiple of 3", (long long)n_vn);
-  if (n_face <= 0 || n_face % 10) return fail(c, B200RT_ERR_INVALID, "face_data length %lld is not a positive multiple of 10", (long long)n_face);
-  if (n_bvh <= 0 || n_bvh % 9) return fail(c, B200RT_ERR_INVALID, "BVH length %lld is not a positive multiple of 9", (long long)n_bvh);
-  if (n_bvh / 9 >= (1 << 24)) return fail(c, B200RT_ERR_UNSUPPORTED, "%lld nodes: float32-encoded child indices are exact only below 2^24 (BVH.py:165)", (long long)(n_bvh / 9));
-  if (n_mat <= 0 || n_mat % 6) return fail(c, B200RT_ERR_INVALID, "material_data must hold 6 floats per material (got %lld)", (long long)n_mat);
+}  // extern "C"
 
+namespace {
+
+struct SceneArgs {
+  const float *vp; int64_t n_vp;
+  const float *vn; int64_t n_vn;
+  const int32_t *face; int64_t n_face;
+  const float *mat; int64_t n_mat;
+  const float *bvh; int64_t n_bvh;
+};
+
+// shape checks of the reference-layout buffers; the message goes to the context (or to the create-error slot)
+int check_scene_args(b200rt_ctx *c, const SceneArgs &a) {
+  if (!a.vp || !a.vn || !a.face || !a.mat || !a.bvh) return fail(c, B200RT_ERR_INVALID, "NULL scene buffer");
+  if (a.n_vp <= 0 || a.n_vp % 3) return fail(c, B200RT_ERR_INVALID, "vertex_p length %lld is not a positive multiple of 3", (long long)a.n_vp);
+  if (a.n_vn <= 0 || a.n_vn % 3) return fail(c, B200RT_ERR_INVALID, "vertex_n length %lld is not a positive multiple of 3", (long long)a.n_vn);
+  if (a.n_face <= 0 || a.n_face % 10) return fail(c, B200RT_ERR_INVALID, "face_data length %lld is not a positive multiple of 10", (long long)a.n_face);
+  if (a.n_bvh <= 0 || a.n_bvh % 9) return fail(c, B200RT_ERR_INVALID, "BVH length %lld is not a positive multiple of 9", (long long)a.n_bvh);
+  if (a.n_bvh / 9 >= (1 << 24)) return fail(c, B200RT_ERR_UNSUPPORTED, "%lld nodes: float32-encoded child indices are exact only below 2^24 (BVH.py:165)", (long long)(a.n_bvh / 9));
+  if (a.n_mat <= 0 || a.n_mat % 6) return fail(c, B200RT_ERR_INVALID, "material_data must hold 6 floats per material (got %lld)", (long long)a.n_mat);
+  return 0;
+}
+
+uint64_t scene_hash_of(const SceneArgs &a) {
   uint64_t h = 0x7363656e65ull;
-  h = hash_bytes(vp, (size_t)n_vp * 4, h);
-  h = hash_bytes(vn, (size_t)n_vn * 4, h);
-  h = hash_bytes(face, (size_t)n_face * 4, h);
-  h = hash_bytes(bvh, (size_t)n_bvh * 4, h);
-  if (c->have_scene && c->have_scene_cached && h == c->scene_hash) {  // geometry unchanged (the UI rebuilds identical arrays per render, UI.py:98)
-    int rc = b200rt_set_materials(c, mat, n_mat);
-    c->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    return rc;
-  }
+  h = hash_bytes(a.vp, (size_t)a.n_vp * 4, h);
+  h = hash_bytes(a.vn, (size_t)a.n_vn * 4, h);
+  h = hash_bytes(a.face, (size_t)a.n_face * 4, h);
+  h = hash_bytes(a.bvh, (size_t)a.n_bvh * 4, h);
+  return h;
+}
 
+bool scene_is_cached(const b200rt_ctx *c, uint64_t h) { return c->have_scene && c->have_scene_cached && h == c->scene_hash; }
+
+// Copies a repacked scene to the context's GPU and, only after every copy has succeeded, commits the fields the
+// kernels' launch geometry and margins derive from.  `R` is shared by every GPU of a multi-GPU handle.
+int upload_scene(b200rt_ctx *c, const Repacked &R, const SceneArgs &a, uint64_t h) {
   // From here on the context describes no scene until the new one is complete: a caller that catches an error and
-  // resubmits the previous scene must not hit the content-hash shortcut above with half-replaced buffers.
+  // resubmits the previous scene must not hit the content-hash shortcut with half-replaced buffers.
   c->have_scene = false;
   c->have_scene_cached = false;
   c->scene_hash = 0;
-
-  const int n_nodes = (int)(n_bvh / 9), n_tris = (int)(n_face / 10);
-  Repacked R;
-  {
-    std::string msg;
-    int rc = repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_mat / 6, bvh, n_bvh, &R, &msg);
-    if (rc) return fail(c, rc, "%s", msg.c_str());
-  }
-
-  // ---- upload -------------------------------------------------------------------------------------------------------------
+  const int n_tris = R.n_tris;
   CU(cudaSetDevice(c->device));
   if (ensure(c, c->d_tris, R.tris.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_normals, R.normals.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_tboxes, R.tboxes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_frames, (size_t)n_tris * kFrameVec * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_nodes, R.nodes.size() * sizeof(uint4))) return B200RT_ERR_CUDA;
-  if (ensure(c, c->d_bvh9, (size_t)n_bvh * 4)) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_bvh9, (size_t)a.n_bvh * 4)) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_leafcnt, R.leaf_count.size() * sizeof(int32_t))) return B200RT_ERR_CUDA;
   CU(cudaMemcpyAsync(c->d_leafcnt.p, R.leaf_count.data(), R.leaf_count.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_tris.p, R.tris.data(), R.tris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -637,13 +659,12 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   CU(cudaMemcpyAsync(c->d_tboxes.p, R.tboxes.data(), R.tboxes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   if (!R.nodes.empty())
     CU(cudaMemcpyAsync(c->d_nodes.p, R.nodes.data(), R.nodes.size() * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_bvh9.p, bvh, (size_t)n_bvh * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_bvh9.p, a.bvh, (size_t)a.n_bvh * 4, cudaMemcpyHostToDevice, c->stream));
   k_tri_frames<<<(n_tris + 127) / 128, 128, 0, c->stream>>>(static_cast<const float4 *>(c->d_normals.p), n_tris,
                                                            static_cast<float4 *>(c->d_frames.p));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
-  // ---- commit: every field the kernels' launch geometry and margins derive from, together ----------------------------
-  c->n_nodes9 = n_nodes;
+  c->n_nodes9 = R.n_nodes9;
   c->n_inner = R.n_inner;
   c->n_tris = n_tris;
   c->node_f4 = R.node_f4;
@@ -660,21 +681,52 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   c->cull_abs = R.cull_abs;
   c->cmax = R.cmax;
   c->fast_ok = R.fast_ok;
-  c->tri_mat.swap(R.tri_mat);
+  c->tri_mat = R.tri_mat;
   c->mat_hash = 0;
   c->n_mats = 0;
-  int rc = b200rt_set_materials(c, mat, n_mat);
+  int rc = b200rt_set_materials(c, a.mat, a.n_mat);
   if (rc) return rc;
   c->have_scene = true;
   c->have_scene_cached = true;
   c->scene_hash = h;
   c->stats.repack_ms = (float)(R.ms_tris + R.ms_walk + R.ms_nodes);
   c->stats.ref_stack_need = c->ref_stack_need;
-  c->stats.nodes = n_nodes;
+  c->stats.nodes = R.n_nodes9;
   c->stats.triangles = n_tris;
   c->stats.bvh_depth = c->depth;
-  c->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const float *vuv,
+                     int64_t n_vuv, const int32_t *face, int64_t n_face, const float *mat, int64_t n_mat,
+                     const int32_t *light, int64_t n_light, const float *bvh, int64_t n_bvh) {
+  (void)vuv; (void)n_vuv; (void)light; (void)n_light;  // fetched / passed but never used by the kernel (MathLib.cl:217, Raytracing.cl:163)
+  if (!c) return B200RT_ERR_INVALID;
+  auto t0 = std::chrono::steady_clock::now();
+  const SceneArgs a{vp, n_vp, vn, n_vn, face, n_face, mat, n_mat, bvh, n_bvh};
+  int rc = check_scene_args(c, a);
+  if (rc) return rc;
+  const uint64_t h = scene_hash_of(a);
+  if (scene_is_cached(c, h)) {  // geometry unchanged (the UI rebuilds identical arrays per render, UI.py:98)
+    rc = b200rt_set_materials(c, mat, n_mat);
+  } else {
+    Repacked R;
+    std::string msg;
+    rc = repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_mat / 6, bvh, n_bvh, &R, &msg);
+    if (rc) {
+      c->have_scene = false;   // as before an upload: the context describes no scene after a rejected one
+      c->have_scene_cached = false;
+      c->scene_hash = 0;
+      return fail(c, rc, "%s", msg.c_str());
+    }
+    rc = upload_scene(c, R, a, h);
+  }
+  c->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
 }
 
 int b200rt_set_ibl(b200rt_ctx *c, const uint8_t *rgba, int width, int height) {
@@ -1007,3 +1059,308 @@ int b200rt_ipc_close(b200rt_ctx *c, void *d_ptr) {
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// Multi-GPU handle: one host process, one context + stream per GPU, NVLink peer reads for the reduce
+// ================================================================================================
+// the frame is divided among the GPUs of one NVSwitch box — by contiguous sample ranges with the
+// counter-based generator, by interleaved rows of 8x4-pixel tiles with the reference's serial per-pixel generator —
+// every GPU renders raw per-pixel sums into its own buffer, and ONE kernel on the first GPU reads all of them through
+// peer mappings (NVLink loads), sums in GPU order, divides by spp and clamps (k_reduce_finalize).  Kernel launches
+// are issued by one host thread per GPU: a frame is thousands of small launches, and a single thread feeding eight
+// GPUs would be the bottleneck.
+struct b200rt_multi {
+  std::vector<b200rt_ctx *> ctx;
+  std::vector<cudaEvent_t> done;   // per GPU: its partial sums are complete
+  std::vector<int> peer_ok;        // GPU 0 can read GPU i's memory directly
+  std::vector<DevBuf> staging;     // on GPU 0, for GPUs it cannot read directly
+  DevBuf d_final;                  // on GPU 0
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // on GPU 0's stream, around wait + reduce
+  std::string err;
+  b200rt_stats stats;
+};
+
+namespace {
+
+int mfail(b200rt_multi *m, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (m) m->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define MCU(call)                                                                                    \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return mfail(m, B200RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// what GPU `r` of `n` renders (ensem3a_openclraytracer_b200/multigpu.py::rank_work is the same rule)
+void multi_share(int r, int n, int spp, int rng_mode, b200rt_opts *o) {
+  o->output = B200RT_OUT_SUMS;
+  if (rng_mode == B200RT_RNG_PHILOX) {
+    const int base = spp / n, extra = spp % n;
+    const int s0 = r * base + (r < extra ? r : extra);
+    o->sample_begin = s0;
+    o->sample_end = s0 + base + (r < extra ? 1 : 0);
+    o->tile_row_mod = 0;
+    o->tile_row_rem = 0;
+  } else {
+    o->sample_begin = 0;
+    o->sample_end = spp;
+    o->tile_row_mod = n > 1 ? n : 0;
+    o->tile_row_rem = n > 1 ? r : 0;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *b200rt_multi_last_error(const b200rt_multi *m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+void b200rt_multi_destroy(b200rt_multi *m) {
+  if (!m) return;
+  if (!m->ctx.empty() && m->ctx[0]) {
+    cudaSetDevice(m->ctx[0]->device);
+    cudaStreamSynchronize(m->ctx[0]->stream);
+    for (DevBuf &b : m->staging)
+      if (b.p) cudaFree(b.p);
+    if (m->d_final.p) cudaFree(m->d_final.p);
+    if (m->ev_begin) cudaEventDestroy(m->ev_begin);
+    if (m->ev_end) cudaEventDestroy(m->ev_end);
+  }
+  for (size_t i = 0; i < m->ctx.size(); ++i) {
+    if (!m->ctx[i]) continue;
+    if (i < m->done.size() && m->done[i]) {
+      cudaSetDevice(m->ctx[i]->device);
+      cudaEventDestroy(m->done[i]);
+    }
+    b200rt_destroy(m->ctx[i]);
+  }
+  delete m;
+}
+
+int b200rt_multi_create(const int *devices, int n_devices, b200rt_multi **out) {
+  b200rt_multi *m = nullptr;
+  if (!out) return mfail(nullptr, B200RT_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!devices || n_devices < 1 || n_devices > 16) return mfail(nullptr, B200RT_ERR_INVALID, "1..16 devices expected (got %d)", n_devices);
+  for (int i = 0; i < n_devices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return mfail(nullptr, B200RT_ERR_INVALID, "device %d listed twice", devices[i]);
+  m = new b200rt_multi();
+  memset(&m->stats, 0, sizeof m->stats);
+  m->ctx.assign((size_t)n_devices, nullptr);
+  m->done.assign((size_t)n_devices, nullptr);
+  m->peer_ok.assign((size_t)n_devices, 1);
+  m->staging.resize((size_t)n_devices);
+  for (int i = 0; i < n_devices; ++i) {
+    int rc = b200rt_create(devices[i], &m->ctx[i]);   // leaves its message in the create-error slot
+    if (rc) { b200rt_multi_destroy(m); return rc; }
+    cudaError_t e = cudaEventCreateWithFlags(&m->done[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { mfail(nullptr, B200RT_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); b200rt_multi_destroy(m); return B200RT_ERR_CUDA; }
+  }
+  cudaSetDevice(devices[0]);
+  for (int i = 1; i < n_devices; ++i) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
+    if (can) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[i], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      can = (e == cudaSuccess);
+      if (!can) cudaGetLastError();
+    }
+    m->peer_ok[i] = can;
+  }
+  if (cudaEventCreate(&m->ev_begin) != cudaSuccess || cudaEventCreate(&m->ev_end) != cudaSuccess) {
+    mfail(nullptr, B200RT_ERR_CUDA, "cudaEventCreate failed");
+    b200rt_multi_destroy(m);
+    return B200RT_ERR_CUDA;
+  }
+  *out = m;
+  return 0;
+}
+
+int b200rt_multi_device_count(const b200rt_multi *m) { return m ? (int)m->ctx.size() : 0; }
+
+b200rt_ctx *b200rt_multi_context(b200rt_multi *m, int index) {
+  if (!m || index < 0 || index >= (int)m->ctx.size()) return nullptr;
+  return m->ctx[index];
+}
+
+int b200rt_multi_set_scene(b200rt_multi *m, const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const float *vuv,
+                           int64_t n_vuv, const int32_t *face, int64_t n_face, const float *mat, int64_t n_mat,
+                           const int32_t *light, int64_t n_light, const float *bvh, int64_t n_bvh) {
+  (void)vuv; (void)n_vuv; (void)light; (void)n_light;
+  if (!m) return B200RT_ERR_INVALID;
+  auto t0 = std::chrono::steady_clock::now();
+  const SceneArgs a{vp, n_vp, vn, n_vn, face, n_face, mat, n_mat, bvh, n_bvh};
+  int rc = check_scene_args(m->ctx[0], a);
+  if (rc) { m->err = m->ctx[0]->err; return rc; }
+  const uint64_t h = scene_hash_of(a);
+  bool all_cached = true;
+  for (b200rt_ctx *c : m->ctx) all_cached = all_cached && scene_is_cached(c, h);
+  Repacked R;
+  if (!all_cached) {  // validated and repacked once, uploaded to every GPU
+    std::string msg;
+    rc = repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_mat / 6, bvh, n_bvh, &R, &msg);
+    if (rc) {
+      for (b200rt_ctx *c : m->ctx) { c->have_scene = false; c->have_scene_cached = false; c->scene_hash = 0; }
+      return mfail(m, rc, "%s", msg.c_str());
+    }
+  }
+  const int n = (int)m->ctx.size();
+  std::vector<int> rcs((size_t)n, 0);
+#pragma omp parallel for num_threads(n) schedule(static, 1)
+  for (int i = 0; i < n; ++i) {
+    b200rt_ctx *c = m->ctx[i];
+    rcs[i] = scene_is_cached(c, h) ? b200rt_set_materials(c, mat, n_mat) : upload_scene(c, R, a, h);
+  }
+  for (int i = 0; i < n; ++i)
+    if (rcs[i]) return mfail(m, rcs[i], "GPU %d: %s", m->ctx[i]->device, m->ctx[i]->err.c_str());
+  m->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  m->stats.nodes = m->ctx[0]->stats.nodes;
+  m->stats.triangles = m->ctx[0]->stats.triangles;
+  m->stats.bvh_depth = m->ctx[0]->stats.bvh_depth;
+  m->stats.repack_ms = m->ctx[0]->stats.repack_ms;
+  m->stats.ref_stack_need = m->ctx[0]->stats.ref_stack_need;
+  return 0;
+}
+
+int b200rt_multi_set_ibl(b200rt_multi *m, const uint8_t *rgba, int width, int height) {
+  if (!m) return B200RT_ERR_INVALID;
+  const int n = (int)m->ctx.size();
+  std::vector<int> rcs((size_t)n, 0);
+#pragma omp parallel for num_threads(n) schedule(static, 1)
+  for (int i = 0; i < n; ++i) rcs[i] = b200rt_set_ibl(m->ctx[i], rgba, width, height);
+  for (int i = 0; i < n; ++i)
+    if (rcs[i]) return mfail(m, rcs[i], "GPU %d: %s", m->ctx[i]->device, m->ctx[i]->err.c_str());
+  return 0;
+}
+
+int b200rt_multi_invalidate(b200rt_multi *m) {
+  if (!m) return B200RT_ERR_INVALID;
+  for (b200rt_ctx *c : m->ctx) b200rt_invalidate(c);
+  return 0;
+}
+
+int b200rt_multi_render(b200rt_multi *m, const float *cam, const float *env, int width, int height, int spp, int max_bounce,
+                        const b200rt_opts *opts, float *out) {
+  if (!m) return B200RT_ERR_INVALID;
+  if (!out) return mfail(m, B200RT_ERR_INVALID, "out_rgb is NULL");
+  if (width <= 0 || height <= 0) return mfail(m, B200RT_ERR_INVALID, "bad frame size %d x %d", width, height);
+  b200rt_opts o;
+  if (opts) o = *opts; else b200rt_default_opts(&o);
+  if (o.output != B200RT_OUT_FINAL || o.sample_end > 0 || o.tile_row_mod > 1)
+    return mfail(m, B200RT_ERR_INVALID, "the multi-GPU handle divides the frame itself: leave output / sample range / tile rows at their defaults");
+  const int n = (int)m->ctx.size();
+  const size_t npix = (size_t)width * height, bytes = npix * 3 * sizeof(float);
+  b200rt_ctx *c0 = m->ctx[0];
+  MCU(cudaSetDevice(c0->device));
+  if (m->d_final.cap < bytes) {
+    if (m->d_final.p) cudaFree(m->d_final.p);
+    m->d_final.p = nullptr; m->d_final.cap = 0;
+    MCU(cudaMalloc(&m->d_final.p, bytes));
+    m->d_final.cap = bytes;
+  }
+  // ---- every GPU renders its share into its own buffer; one host thread per GPU issues the launches ------------
+  std::vector<int> rcs((size_t)n, 0);
+  const int tile_rows = (height + 3) / 4;
+#pragma omp parallel for num_threads(n) schedule(static, 1)
+  for (int i = 0; i < n; ++i) {
+    b200rt_ctx *c = m->ctx[i];
+    b200rt_opts oi = o;
+    multi_share(i, n, spp, o.rng_mode, &oi);
+    int rc = 0;
+    if (cudaSetDevice(c->device) != cudaSuccess) rc = B200RT_ERR_CUDA;
+    if (!rc) rc = ensure(c, c->d_out, bytes);
+    if (!rc && cudaMemsetAsync(c->d_out.p, 0, bytes, c->stream) != cudaSuccess) rc = B200RT_ERR_CUDA;
+    const bool empty = (oi.sample_begin == oi.sample_end) || (oi.tile_row_mod > 1 && oi.tile_row_rem >= tile_rows);
+    c->stats.rays = 0; c->stats.samples = 0; c->stats.total_ms = 0; c->stats.kernel_launches = 0;
+    if (!rc && !empty) rc = render_impl(c, cam, env, width, height, spp, max_bounce, &oi, static_cast<float *>(c->d_out.p));
+    if (!rc && cudaEventRecord(m->done[i], c->stream) != cudaSuccess) rc = B200RT_ERR_CUDA;
+    if (rc == B200RT_ERR_CUDA && c->err.empty()) c->err = "CUDA call failed while enqueueing the frame";
+    rcs[i] = rc;
+  }
+  for (int i = 0; i < n; ++i)
+    if (rcs[i]) return mfail(m, rcs[i], "GPU %d: %s", m->ctx[i]->device, m->ctx[i]->err.c_str());
+  // ---- GPU 0: wait for the peers (device-side), then one kernel reads every partial buffer and finalises ----------
+  MCU(cudaSetDevice(c0->device));
+  MCU(cudaEventRecord(m->ev_begin, c0->stream));
+  PartList pl;
+  pl.n = n;
+  for (int i = 0; i < n; ++i) {
+    if (i > 0) MCU(cudaStreamWaitEvent(c0->stream, m->done[i], 0));
+    const float *src = static_cast<const float *>(m->ctx[i]->d_out.p);
+    if (i > 0 && !m->peer_ok[i]) {  // no direct mapping: stage the partial sums on GPU 0
+      DevBuf &sb = m->staging[i];
+      if (sb.cap < bytes) {
+        if (sb.p) cudaFree(sb.p);
+        sb.p = nullptr; sb.cap = 0;
+        MCU(cudaMalloc(&sb.p, bytes));
+        sb.cap = bytes;
+      }
+      MCU(cudaMemcpyPeerAsync(sb.p, c0->device, src, m->ctx[i]->device, bytes, c0->stream));
+      src = static_cast<const float *>(sb.p);
+    }
+    pl.p[i] = src;
+  }
+  const long long nn = (long long)npix * 3;
+  const int grid = (int)std::min<long long>((nn / 4 + 255) / 256 + 1, (long long)c0->sm_count * 8);
+  k_reduce_finalize<<<grid, 256, 0, c0->stream>>>(pl, static_cast<float *>(m->d_final.p), nn / 4, nn, (float)spp);
+  MCU(cudaGetLastError());
+  MCU(cudaEventRecord(m->ev_end, c0->stream));
+  MCU(cudaMemcpyAsync(out, m->d_final.p, bytes, cudaMemcpyDeviceToHost, c0->stream));
+  MCU(cudaStreamSynchronize(c0->stream));
+  // ---- statistics: work summed over the GPUs, device time = the slowest GPU + the reduce ---------------------------
+  b200rt_stats agg = m->stats;
+  const float upload_ms = agg.upload_ms;
+  memset(&agg, 0, sizeof agg);
+  agg.upload_ms = upload_ms;
+  float slowest = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    b200rt_ctx *c = m->ctx[i];
+    if (c->stats_pending) {
+      MCU(cudaSetDevice(c->device));
+      int rc = read_counters(c);
+      if (rc) return mfail(m, rc, "GPU %d: %s", c->device, c->err.c_str());
+    }
+    agg.rays += c->stats.rays;
+    agg.box_tests += c->stats.box_tests;
+    agg.tri_tests += c->stats.tri_tests;
+    agg.mismatches += c->stats.mismatches;
+    agg.samples += c->stats.samples;
+    agg.kernel_launches += c->stats.kernel_launches;
+    agg.revalidated += c->stats.revalidated;
+    agg.exact_walks += c->stats.exact_walks;
+    slowest = std::max(slowest, c->stats.total_ms);
+    agg.primary_ms = std::max(agg.primary_ms, c->stats.primary_ms);
+    agg.trace_ms = std::max(agg.trace_ms, c->stats.trace_ms);
+  }
+  float red = 0.0f;
+  MCU(cudaSetDevice(c0->device));
+  cudaEventElapsedTime(&red, m->ev_begin, m->ev_end);  // includes waiting for the slowest peer after GPU 0 finished
+  agg.total_ms = std::max(slowest, c0->stats.total_ms + red);
+  agg.kernel_launches += 1;
+  agg.nodes = c0->stats.nodes;
+  agg.triangles = c0->stats.triangles;
+  agg.bvh_depth = c0->stats.bvh_depth;
+  agg.scene_in_smem = c0->stats.scene_in_smem;
+  agg.repack_ms = c0->stats.repack_ms;
+  agg.ref_stack_need = c0->stats.ref_stack_need;
+  m->stats = agg;
+  return 0;
+}
+
+int b200rt_multi_get_stats(const b200rt_multi *m, b200rt_stats *s) {
+  if (!m || !s) return B200RT_ERR_INVALID;
+  *s = m->stats;
+  return 0;
+}
+
+}  // extern "C"
+

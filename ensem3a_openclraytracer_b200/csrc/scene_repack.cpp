@@ -7,7 +7,6 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 
 #include "../../include/b200rt.h"
@@ -51,20 +50,21 @@ struct Axis {
   float base, pitch;
 };
 
-// (q, hq) whose decoded box encloses [mn, mx] in real arithmetic
+// (q, hq) whose decoded box encloses [mn, mx] in real arithmetic.  binary64 throughout: fc * pitch is exact (16 x 24
+// bits), the sum with base rounds once (relative 2^-53), and `slack` covers that rounding many times over.
 void quantise(const Axis &g, float mn, float mx, uint32_t *q_out, float *hq_out) {
-  const long double base = g.base, pitch = g.pitch;
-  const long double mid = 0.5L * ((long double)mn + (long double)mx);
-  long double qf = ((mid - base) / pitch - 0.5L) * 65536.0L;
-  long long q = (long long)std::floor((double)qf + 0.5);
-  q = std::min<long long>(std::max<long long>(q, 0), 32767);
-  const long double fc = 0.5L + (long double)q / 65536.0L;
-  const long double c = base + fc * pitch;  // the product is exact (16 x 24 bits); the sum may round in the 64th bit
-  const long double slack = (std::fabs(base) + pitch) * 0x1p-58L;
-  const long double need = std::max(c - (long double)mn, (long double)mx - c) + slack;
-  float hq = bf16_up((double)(need / pitch) * (1.0 + 0x1p-40));
-  while ((long double)hq * pitch < need) hq = as_float(as_u32(hq) + 0x10000u);
-  *q_out = (uint32_t)q;
+  const double base = g.base, pitch = g.pitch;
+  const double mid = 0.5 * ((double)mn + (double)mx);
+  double qf = std::floor(((mid - base) / pitch - 0.5) * 65536.0 + 0.5);
+  if (!(qf >= 0.0)) qf = 0.0;
+  if (qf > 32767.0) qf = 32767.0;
+  const double fc = 0.5 + qf / 65536.0;
+  const double c = base + fc * pitch;
+  const double slack = (std::fabs(base) + pitch) * 0x1p-48;
+  const double need = std::max(c - (double)mn, (double)mx - c) + slack;
+  float hq = bf16_up((need / pitch) * (1.0 + 0x1p-40));
+  while ((double)hq * pitch < need) hq = as_float(as_u32(hq) + 0x10000u);
+  *q_out = (uint32_t)qf;
   *hq_out = hq;
 }
 
@@ -82,7 +82,7 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
   // ---- triangles: validate indices, precompute edges exactly as MathLib.cl:129-130 rounds them ------------------
   R.tris.resize((size_t)n_tris * 3);
   R.normals.resize((size_t)n_tris);
-  R.tboxes.assign((size_t)n_tris * 2, Repacked::f4{0, 0, 0, 0});
+  R.tboxes.resize((size_t)n_tris * 2);
   R.tri_mat.resize((size_t)n_tris);
   float cmax = 0.0f;
   int first_bad = n_tris;   // first triangle with an out-of-range index
@@ -105,6 +105,8 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
     R.tris[3 * (size_t)t + 2] = Repacked::f4{e2z, as_float((uint32_t)f[0]), unranked, 0.0f};
     const float *n0 = vn + 3 * (size_t)f[4];
     R.normals[t] = Repacked::f4{n0[0], n0[1], n0[2], 0.0f};
+    R.tboxes[2 * (size_t)t] = Repacked::f4{0, 0, 0, 0};   // stays empty if no leaf holds the triangle
+    R.tboxes[2 * (size_t)t + 1] = Repacked::f4{0, 0, 0, 0};
     R.tri_mat[t] = f[0];
     for (int j = 7; j < 10; ++j)
       for (int k = 0; k < 3; ++k) {
@@ -139,7 +141,104 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
   auto T = [&](int i) { return (int)bvh[9 * (size_t)i + 8]; };
   int depth = 0;
   size_t max_stack = 1;
+  std::vector<int> first_rank;    // id-ordered trees: rank of the first leaf under each node
+  // ---- fast path: a tree whose children always carry larger ids than their parent (what BVH.py and the native
+  // builder emit: children are appended at split time).  Everything the serial walk below derives then follows from
+  // passes over the node array in id order — per-node checks in parallel, depth / pending-stack / first-rank top-down,
+  // leaves per sub-tree bottom-up — instead of one pointer-chasing walk over ten million nodes.
+  bool id_ordered = n_nodes >= 1;
+  {
+    int bad = 0, noncanon = 0, nf = 0;
+    float cm = cmax;
+    std::vector<int> indeg((size_t)n_nodes, 0);
+#pragma omp parallel for schedule(static) reduction(| : bad, noncanon, nf) reduction(max : cm)
+    for (int i = 0; i < n_nodes; ++i) {
+      const float *rec = bvh + 9 * (size_t)i;
+      const int l = (int)rec[0], r = (int)rec[1], t = (int)rec[8];
+      if (t < -1 || t >= n_tris || l < -1 || r < -1 || l >= n_nodes || r >= n_nodes || (l != -1 && l <= i) || (r != -1 && r <= i) ||
+          (l != -1 && l == r)) {
+        bad |= 1;
+        continue;
+      }
+      const float *bx = rec + 2;
+      for (int k = 0; k < 6; ++k) {
+        const float v = std::fabs(bx[k]);
+        if (!std::isfinite(v)) nf |= 1;
+        else if (v > cm) cm = v;
+      }
+      const bool leaf = (t != -1 && l == -1 && r == -1), inner = (t == -1 && l != -1 && r != -1);
+      if (!leaf && !inner) noncanon |= 1;
+      for (int k = 0; k < 3; ++k)
+        if (!(bx[k] <= bx[k + 3])) noncanon |= 1;
+      for (int ch : {l, r})
+        if (ch != -1) {
+          const float *cb = bvh + 9 * (size_t)ch + 2;
+          for (int k = 0; k < 3; ++k)
+            if (!(cb[k] >= bx[k] && cb[k + 3] <= bx[k + 3])) noncanon |= 1;
+#pragma omp atomic
+          indeg[ch]++;
+        }
+    }
+    if (bad) id_ordered = false;
+    if (id_ordered) {
+      int wrong = indeg[0] != 0 ? 1 : 0;
+#pragma omp parallel for schedule(static) reduction(| : wrong)
+      for (int i = 1; i < n_nodes; ++i)
+        if (indeg[i] != 1) wrong |= 1;   // unreachable or shared nodes: let the walk below decide what to report
+      if (wrong) id_ordered = false;
+    }
+    if (id_ordered) {
+      if (nf) nonfinite |= 1;
+      if (noncanon) canonical = false;
+      cmax = cm;
+      // top-down in id order: level, entries pending on the reference's stack when the node is popped, first leaf rank
+      std::vector<int> level((size_t)n_nodes, 0), pending((size_t)n_nodes, 0);
+      R.leaf_count.resize((size_t)n_nodes);
+      for (int i = n_nodes - 1; i >= 0; --i) {
+        const float *rec = bvh + 9 * (size_t)i;
+        const int l = (int)rec[0], r = (int)rec[1];
+        R.leaf_count[i] = ((int)rec[8] != -1 ? 1 : 0) + (l != -1 ? R.leaf_count[l] : 0) + (r != -1 ? R.leaf_count[r] : 0);
+      }
+      first_rank.assign((size_t)n_nodes, 0);
+      for (int i = 0; i < n_nodes; ++i) {
+        const float *rec = bvh + 9 * (size_t)i;
+        const int l = (int)rec[0], r = (int)rec[1];
+        if (level[i] > depth) depth = level[i];
+        const size_t pushed = (size_t)pending[i] + (l != -1 ? 1 : 0) + (r != -1 ? 1 : 0);
+        if (pushed > max_stack) max_stack = pushed;
+        // the reference pushes left then right and pops right first (MathLib.cl:275-280): the right sub-tree is walked
+        // with the left child still on the stack and takes the lower ranks; a node's own triangle comes before both
+        const int own = (int)rec[8] != -1 ? 1 : 0;
+        if (r != -1) {
+          level[r] = level[i] + 1;
+          pending[r] = pending[i] + (l != -1 ? 1 : 0);
+          first_rank[r] = first_rank[i] + own;
+        }
+        if (l != -1) {
+          level[l] = level[i] + 1;
+          pending[l] = pending[i];
+          first_rank[l] = first_rank[i] + own + (r != -1 ? R.leaf_count[r] : 0);
+        }
+      }
+      int dup = 0;
+#pragma omp parallel for schedule(static) reduction(| : dup)
+      for (int i = 0; i < n_nodes; ++i) {
+        const float *rec = bvh + 9 * (size_t)i;
+        const int t = (int)rec[8];
+        if (t == -1) continue;
+        uint32_t *slot = reinterpret_cast<uint32_t *>(&R.tris[3 * (size_t)t + 2].z);
+        uint32_t old;
+#pragma omp atomic capture
+        { old = *slot; *slot = (uint32_t)first_rank[i]; }
+        if (old != 0x7fffffffu) { dup |= 1; continue; }   // a triangle held by two leaves: rank and box ambiguous
+        R.tboxes[2 * (size_t)t] = Repacked::f4{rec[2], rec[3], rec[4], 0.0f};
+        R.tboxes[2 * (size_t)t + 1] = Repacked::f4{rec[5], rec[6], rec[7], 0.0f};
+      }
+      if (dup) canonical = false;
+    }
+  }
   std::vector<int> preorder;
+  if (!id_ordered) {
   preorder.reserve((size_t)n_nodes);
   {
     // right-first pre-order walk == the order MathLib.cl:252-280 pops nodes when every box test passes
@@ -218,6 +317,7 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
     const int l = (int)rec[0], r = (int)rec[1];
     R.leaf_count[cur] = ((int)rec[8] != -1 ? 1 : 0) + (l != -1 ? R.leaf_count[l] : 0) + (r != -1 ? R.leaf_count[r] : 0);
   }
+  }  // !id_ordered
   R.depth = depth;
   R.ref_stack_need = (int)max_stack;
   if (R.ref_stack_need > kRefStackMax) canonical = false;  // closest_hit_nodrop's thread-local stack
@@ -277,16 +377,15 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
       order.reserve((size_t)n_nodes / 2 + 1);
       order.push_back(0);
       inner_id[0] = 0;
-      if (const char *e = getenv("B200RT_NODE_ORDER"); e && e[0] == 'b') {  // experiment: breadth-first
-        for (size_t q = 0; q < order.size(); ++q) {
-          const int cur = order[q];
-          const int ch[2] = {L(cur), Rc(cur)};
-          for (int k = 0; k < 2; ++k)
-            if (T(ch[k]) == -1) {
-              inner_id[ch[k]] = (int)order.size();
-              order.push_back(ch[k]);
-            }
-        }
+      if (id_ordered) {
+        // BVH.py appends both children at split time and then builds the left sub-tree completely (BVH.py:107-109,
+        // 147-153): interior nodes in id order ARE the pre-order over sibling pairs
+        order.clear();
+        for (int i = 0; i < n_nodes; ++i)
+          if (T(i) == -1) {
+            inner_id[i] = (int)order.size();
+            order.push_back(i);
+          }
       } else {
         std::vector<int> todo;
         todo.push_back(0);
@@ -308,7 +407,7 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
       // small scenes are staged in shared memory with 48-byte node spacing (SceneView::node_f4)
       const int nf4 = ((size_t)n_inner * 48 + (size_t)n_tris * 48 <= kSmemSceneMax) ? 3 : 2;
       R.node_f4 = nf4;
-      R.nodes.assign((size_t)n_inner * nf4, Repacked::u4{0, 0, 0, 0});
+      R.nodes.resize((size_t)n_inner * nf4);
 #pragma omp parallel for schedule(static)
       for (int q = 0; q < n_inner; ++q) {
         const int cur = order[q];
@@ -336,6 +435,7 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
         b.w = (uint32_t)refr;
         R.nodes[(size_t)nf4 * q + 0] = a;
         R.nodes[(size_t)nf4 * q + 1] = b;
+        if (nf4 == 3) R.nodes[(size_t)nf4 * q + 2] = Repacked::u4{0, 0, 0, 0};
       }
     }
   }
@@ -360,6 +460,7 @@ extern "C" int b200rt_repack_probe(const float *vp, int64_t n_vp, const float *v
   for (int k = 0; k < 3; ++k) {
     info[8 + k] = R.grid_base[k]; info[11 + k] = R.grid_pitch[k]; info[14 + k] = R.root_fc[k]; info[17 + k] = R.root_hq[k];
   }
+  info[20] = (float)R.ms_tris; info[21] = (float)R.ms_walk; info[22] = (float)R.ms_nodes; info[23] = 0.0f;
   if (nodes_out) {
     if (n_nodes_out < (int64_t)R.n_inner * 8) return B200RT_ERR_INVALID;
     for (int q = 0; q < R.n_inner; ++q) {

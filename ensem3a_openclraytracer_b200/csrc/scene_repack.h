@@ -3,18 +3,32 @@
 // after every copy has succeeded.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
 namespace b200rt {
 
+// std::vector that leaves trivially-constructible elements uninitialised on resize(): the repacked arrays of a
+// 5 M-triangle scene are ~1 GB, every element is written by the (parallel) loops, and a serial zero-fill first would
+// cost more than those loops.
+template <class T>
+struct raw_alloc : std::allocator<T> {
+  template <class U> struct rebind { using other = raw_alloc<U>; };
+  raw_alloc() = default;
+  template <class U> raw_alloc(const raw_alloc<U> &) {}
+  template <class U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using raw_vector = std::vector<T, raw_alloc<T>>;
+
 struct Repacked {
   struct f4 { float x, y, z, w; };
   struct u4 { uint32_t x, y, z, w; };
-  std::vector<u4> nodes;        // node_f4 x 16 bytes per interior node (rt_trace.cuh "repacked scene")
-  std::vector<f4> tris, normals, tboxes;
+  raw_vector<u4> nodes;         // node_f4 x 16 bytes per interior node (rt_trace.cuh "repacked scene")
+  raw_vector<f4> tris, normals, tboxes;
   std::vector<int32_t> tri_mat;
-  std::vector<int32_t> leaf_count;  // per node of the as-is array: leaves in its sub-tree (validate_chain, rt_trace.cuh)
+  raw_vector<int32_t> leaf_count;  // per node of the as-is array: leaves in its sub-tree (validate_chain, rt_trace.cuh)
   int n_nodes9 = 0, n_inner = 0, n_tris = 0;
   int node_f4 = 2;              // 2 in global memory, 3 when nodes + triangles fit the shared-memory staging area
   int depth = 0, ref_stack_need = 0;

@@ -190,17 +190,46 @@ int b200rt_ipc_close(b200rt_ctx *ctx, void *d_ptr);
 int b200rt_build_bvh(const float *vertex_p, int64_t n_vertex_p, const int32_t *face_data, int64_t n_face_data,
                      float *bvh_out, int64_t n_bvh_out, int32_t *depth_out);
 
+/* ---- several GPUs of one NVSwitch box behind one handle (one host process) ---------------------------------------
+ * What SURVEY.md 8b asks of the boundary: the call main.py makes (KernelLauncher.launch_Raytracing, KernelLauncher.py:33)
+ * can own 1, 2, 4 or 8 GPUs.  Scene and environment are replicated; the frame is divided by contiguous sample ranges
+ * with B200RT_RNG_PHILOX (image equal to the one-GPU image up to the order of the float additions) and by interleaved
+ * rows of 8x4-pixel tiles with B200RT_RNG_REFERENCE (bit-identical); the per-GPU partial sums are read over NVLink by
+ * one reduce + finalize kernel on the first GPU.  Same argument meaning as the single-GPU calls above; opts must leave
+ * output, sample range and tile rows at their defaults.  b200rt_multi_context lends the per-GPU context (index 0 is
+ * the GPU that holds the final image) for the calls that need no partition, e.g. b200rt_img_processing. */
+typedef struct b200rt_multi b200rt_multi;
+int b200rt_multi_create(const int *devices, int n_devices, b200rt_multi **out);
+void b200rt_multi_destroy(b200rt_multi *m);
+const char *b200rt_multi_last_error(const b200rt_multi *m); /* m may be NULL: last create error */
+int b200rt_multi_device_count(const b200rt_multi *m);
+b200rt_ctx *b200rt_multi_context(b200rt_multi *m, int index);
+int b200rt_multi_set_scene(b200rt_multi *m, const float *vertex_p, int64_t n_vertex_p, const float *vertex_n,
+                           int64_t n_vertex_n, const float *vertex_uv, int64_t n_vertex_uv, const int32_t *face_data,
+                           int64_t n_face_data, const float *material_data, int64_t n_material_data,
+                           const int32_t *light_data, int64_t n_light_data, const float *bvh, int64_t n_bvh);
+int b200rt_multi_set_ibl(b200rt_multi *m, const uint8_t *rgba, int width, int height);
+int b200rt_multi_invalidate(b200rt_multi *m);
+int b200rt_multi_render(b200rt_multi *m, const float *cam, const float *env, int width, int height, int spp,
+                        int max_bounce, const b200rt_opts *opts, float *out_rgb);
+/* rays / samples / launches summed over the GPUs (every GPU traces the frame's primary rays once); total_ms = the
+ * slowest GPU, reduce included */
+int b200rt_multi_get_stats(const b200rt_multi *m, b200rt_stats *stats);
+
 /* Host-only view of what b200rt_set_scene uploads (no context, no GPU): validates the buffers exactly as
  * b200rt_set_scene does and writes the repacked interior-node records (8 x uint32 each, csrc/rt_trace.cuh "repacked
- * scene") to nodes_out (capacity in uint32 words; may be NULL to query).  info_out (20 floats): [0] interior nodes,
+ * scene") to nodes_out (capacity in uint32 words; may be NULL to query).  info_out (24 floats): [0] interior nodes,
  * [1] 16-byte units per node, [2] tree depth, [3] stack entries the reference-order walk needs, [4] canonical (fast
  * traversal applies), [5] fast_ok, [6] cmax, [7] cull_abs, [8..10] grid base, [11..13] grid pitch, [14..16] root fc,
- * [17..19] root hq.  Lets the CPU test-suite check that every quantised box encloses the exact one. */
+ * [17..19] root hq, [20..22] host milliseconds of the three stages (triangles, tree walk, node records).  Lets the CPU test-suite check that every quantised box encloses the exact one. */
 int b200rt_repack_probe(const float *vertex_p, int64_t n_vertex_p, const float *vertex_n, int64_t n_vertex_n,
                         const int32_t *face_data, int64_t n_face_data, int64_t n_materials, const float *bvh,
                         int64_t n_bvh, uint32_t *nodes_out, int64_t n_nodes_out, float *info_out);
 
 const char *b200rt_version(void);
+
+/* CUDA devices visible to the process (0 without a usable driver / GPU). */
+int b200rt_device_count(void);
 
 #ifdef __cplusplus
 }

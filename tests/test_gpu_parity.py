@@ -27,8 +27,12 @@ def bits(a):
 
 
 def assert_radiance(out, ref):
-    rel = np.abs(out - ref) / np.maximum(np.abs(ref), REL_FLOOR)
-    assert np.nanmax(rel) <= REL_TOL, f"max relative error {np.nanmax(rel)}"
+    # a value that is NaN on one side only must fail: compare the masks before nanmax skips them
+    assert np.array_equal(np.isnan(out), np.isnan(ref)), "NaN pixels differ"
+    assert np.array_equal(np.isinf(out), np.isinf(ref)), "infinite pixels differ"
+    fin = np.isfinite(ref)
+    rel = np.abs(out[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), REL_FLOOR)
+    assert rel.size == 0 or rel.max() <= REL_TOL, f"max relative error {rel.max()}"
     assert np.mean(bits(out) == bits(ref)) >= IDENTICAL_MIN
 
 
@@ -377,3 +381,132 @@ def test_finalize_and_reduce_kernels(gpu_ctx):
     want = np.fmax(np.fmin(s / np.float32(spp), np.float32(1)), np.float32(0))
     assert np.array_equal(bits(out.cpu().numpy()), bits(want))
     gpu_ctx.set_stream(None)
+
+
+# ---- round 2: holes named by the round-1 review ---------------------------------------------------------------------
+def test_near_parallel_rays_verify_mode(gpu_ctx):
+    """Adversarial for the distance cull of the fast traversal: rays almost parallel to large triangles (|a| of
+    Möller–Trumbore close to its 1e-7 threshold), where the computed hit distance is ill-conditioned, and rays lying in
+    the planes of the Cornell box's walls.  VERIFY mode traces every ray both ways and counts disagreements."""
+    r = np.random.default_rng(5)
+    for name in ("cornell", "proto"):
+        sc = fixtures.load_scene(name)
+        fixtures.upload(gpu_ctx, sc)
+        vp = sc["V_p"].reshape(-1, 3)
+        face = sc["faceData"].reshape(-1, 10)
+        n = 60000
+        t = r.integers(0, face.shape[0], n)
+        a, b, c = vp[face[t, 7]], vp[face[t, 8]], vp[face[t, 9]]
+        nrm = np.cross(b - a, c - a)
+        nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+        u, v = r.uniform(0, 1, (n, 1)), r.uniform(0, 1, (n, 1))
+        flip = (u + v) > 1
+        u, v = np.where(flip, 1 - u, u), np.where(flip, 1 - v, v)
+        inside = a + u * (b - a) + v * (c - a)                                  # a point on the triangle
+        along = (b - a) * r.uniform(-1, 1, (n, 1)) + (c - a) * r.uniform(-1, 1, (n, 1))
+        along /= np.maximum(np.linalg.norm(along, axis=1, keepdims=True), 1e-20)
+        tilt = (10.0 ** r.uniform(-9, -3, (n, 1))) * r.choice([-1.0, 1.0], (n, 1))   # angle to the plane, radians
+        tilt[: n // 6] = 0.0                                                     # exactly in the plane
+        d = along + tilt * nrm
+        back = r.uniform(0.05, 3.0, (n, 1))
+        o = inside - back * d
+        rays = np.concatenate([o, d], axis=1).astype(np.float32)
+        tri, k = gpu_ctx.trace_rays(rays, rt.make_opts(traversal=rt.TRAVERSAL_VERIFY, stack_cap=64))
+        assert gpu_ctx.stats()["mismatches"] == 0, name
+        want_tri, want_k, _ = oracle.trace_rays(sc, rays, stack_cap=64)
+        tri_f, k_f = gpu_ctx.trace_rays(rays, rt.make_opts(traversal=rt.TRAVERSAL_FAST))
+        assert np.array_equal(tri_f, want_tri) and np.array_equal(bits(k_f), bits(want_k)), name
+
+
+def test_axis_aligned_and_in_plane_rays(gpu_ctx):
+    """Zero direction components (whole image columns have them) stay on the fast traversal and are validated along
+    the winner's root-to-leaf chain; rays that lie exactly in a wall's plane hit the 0/0 cases of the reference's slab
+    test (MathLib.cl:169-188).  Bit-exact against the oracle, which divides like the reference."""
+    sc = fixtures.load_scene("cornell")
+    fixtures.upload(gpu_ctx, sc)
+    bvh = sc["BVH"].reshape(-1, 9)
+    lo, hi = bvh[0, 2:5], bvh[0, 5:8]
+    r = np.random.default_rng(9)
+    n = 30000
+    o = r.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = r.standard_normal((n, 3)).astype(np.float32)
+    zero = r.integers(0, 3, n)
+    d[np.arange(n), zero] = 0.0
+    two = r.random(n) < 0.2
+    d[two, (zero[two] + 1) % 3] = 0.0
+    snap = r.random(n) < 0.5                      # origin exactly on a box plane of the scene, on the zeroed axis
+    planes = np.where(r.random(n) < 0.5, lo[zero], hi[zero]).astype(np.float32)
+    o[snap, zero[snap]] = planes[snap]
+    d[r.random(n) < 0.05] *= np.float32(1e-30)    # denormal-range components
+    rays = np.concatenate([o, d], axis=1).astype(np.float32)
+    want_tri, want_k, _ = oracle.trace_rays(sc, rays)
+    for trav in (rt.TRAVERSAL_FAST, rt.TRAVERSAL_REFERENCE):
+        tri, k = gpu_ctx.trace_rays(rays, rt.make_opts(traversal=trav))
+        assert np.array_equal(tri, want_tri), f"{(tri != want_tri).sum()} triangle ids differ (traversal {trav})"
+        assert np.array_equal(bits(k), bits(want_k))
+    # a frame whose centre column has d.x == 0 exactly: no ray leaves the fast path
+    cam, env = fixtures.cam_env(sc["params"], 64)
+    out = gpu_ctx.render(cam, env, 64, 64, 4, 4, opts=rt.make_opts())
+    assert gpu_ctx.stats()["exact_walks"] == 0
+    ref, _ = oracle.render(sc, cam, env, 64 * 64, 4, 4, fixtures.load_ibl())
+    assert np.array_equal(bits(out), bits(ref))
+
+
+def test_8k_environment_map_band_against_oracle(gpu_ctx):
+    """BASELINE config 4's environment: the 8192 x 4096 stand-in (128 MiB) uploaded as a texture; a band of the Serre
+    frame, where most paths end in an environment lookup, against the oracle — both generators."""
+    sc, ibl = fixtures.load_scene("serre"), fixtures.load_ibl("8k")
+    assert ibl.shape == (4096, 8192, 4)
+    fixtures.upload(gpu_ctx, sc, ibl)
+    W, H = 384, 216
+    cam, env = fixtures.cam_env(sc["params"], W, H)
+    i0, i1 = 80 * W, 112 * W
+    for rng, orng in ((rt.RNG_REFERENCE, oracle.RNG_REFERENCE), (rt.RNG_PHILOX, oracle.RNG_PHILOX)):
+        want, _ = oracle.render(sc, cam, env, W * H, 4, 4, ibl, i0=i0, i1=i1, rng_mode=orng, seed=2)
+        out = gpu_ctx.render(cam, env, W, H, 4, 4, opts=rt.make_opts(rng_mode=rng, seed=2, pixel_begin=i0, pixel_end=i1))
+        assert_radiance(out[3 * i0:3 * i1], want[3 * i0:3 * i1])
+        assert np.array_equal(bits(out[3 * i0:3 * i1]), bits(want[3 * i0:3 * i1]))
+    # single texels: directions straight at texel centres of the big map select those texels
+    fixtures.upload(gpu_ctx, sc, fixtures.load_ibl())
+
+
+def test_non_finite_coordinates_are_rejected_anywhere(gpu_ctx):
+    """A NaN or Inf vertex / box plane in the MIDDLE of the arrays (a running max forgets a NaN again)."""
+    sc = fixtures.load_scene("proto")
+    fixtures.upload(gpu_ctx, sc)
+    for key, bad in (("V_p", np.nan), ("V_p", np.inf), ("BVH", np.nan), ("BVH", -np.inf)):
+        arr = sc[key].copy()
+        if key == "V_p":
+            arr[3 * int(sc["faceData"][10 * (sc["faceData"].size // 20) + 8]) + 1] = bad   # a vertex some triangle uses
+        else:
+            arr[9 * (arr.size // 18) + 4] = bad
+        bufs = {k: sc[k] for k in ("V_p", "V_n", "V_uv", "faceData", "materialData", "lightData", "BVH")}
+        bufs[key] = arr
+        with pytest.raises(rt.B200RTError, match="non-finite"):
+            gpu_ctx.set_scene(*[bufs[k] for k in ("V_p", "V_n", "V_uv", "faceData", "materialData", "lightData", "BVH")])
+    # a rejected scene leaves no scene behind (and resubmitting the good one works)
+    cam, env = fixtures.cam_env(sc["params"], 32)
+    with pytest.raises(rt.B200RTError, match="no scene"):
+        gpu_ctx.render(cam, env, 32, 32, 1, 1)
+    fixtures.upload(gpu_ctx, sc)
+    gpu_ctx.render(cam, env, 32, 32, 1, 1)
+
+
+def test_failed_scene_upload_does_not_poison_the_cached_one(gpu_ctx):
+    """set_scene commits its launch geometry only with a complete scene: after a deeper tree is rejected, the
+    previous (shallower) scene resubmitted renders exactly as before."""
+    from tests.synthetic import height_field_scene
+    shallow = fixtures.load_scene("cornell")
+    ibl = fixtures.load_ibl()
+    fixtures.upload(gpu_ctx, shallow, ibl)
+    cam, env = fixtures.cam_env(shallow["params"], 64)
+    before = gpu_ctx.render(cam, env, 64, 64, 3, 4)
+    deep = height_field_scene(48, seed=1)
+    deep["BVH"] = rt.build_bvh(deep["faceData"], deep["V_p"])
+    bad = deep["BVH"].copy()
+    bad[9 * 7 + 3] = np.nan                         # passes the shape checks, fails in the tree walk
+    with pytest.raises(rt.B200RTError):
+        gpu_ctx.set_scene(deep["V_p"], deep["V_n"], deep["V_uv"], deep["faceData"], deep["materialData"], deep["lightData"], bad)
+    fixtures.upload(gpu_ctx, shallow, ibl)
+    after = gpu_ctx.render(cam, env, 64, 64, 3, 4)
+    assert np.array_equal(bits(before), bits(after))
