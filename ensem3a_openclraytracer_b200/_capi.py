@@ -107,7 +107,7 @@ def load_library():
     lib.b200rt_ipc_close.argtypes = [vp, vp]
     lib.b200rt_build_bvh.argtypes = [vp, i64, vp, i64, vp, i64, ctypes.POINTER(ctypes.c_int32)]
     if "b200rt_repack_probe" in SYMBOLS:
-        lib.b200rt_repack_probe.argtypes = [vp, i64, vp, i64, vp, i64, i64, vp, i64, vp, i64, vp]
+        lib.b200rt_repack_probe.argtypes = [vp, i64, vp, i64, vp, i64, i64, vp, i64, vp, i64, vp, vp]
     if "b200rt_multi_create" in SYMBOLS:
         lib.b200rt_multi_create.argtypes = [ctypes.POINTER(ctypes.c_int), i32, ctypes.POINTER(vp)]
         lib.b200rt_multi_destroy.restype = None
@@ -183,18 +183,19 @@ def repack_probe(vertex_p, vertex_n, face_data, n_materials, bvh):
     vp_, vn_, face, bvh_ = _f32(vertex_p), _f32(vertex_n), _i32(face_data), _f32(bvh)
     info = np.zeros(24, np.float32)
     rc = lib.b200rt_repack_probe(_ptr(vp_), vp_.size, _ptr(vn_), vn_.size, _ptr(face), face.size, int(n_materials),
-                                 _ptr(bvh_), bvh_.size, None, 0, _ptr(info))
+                                 _ptr(bvh_), bvh_.size, None, 0, None, _ptr(info))
     if rc != 0:
         raise B200RTError(f"b200rt_repack_probe failed ({rc})")
     nodes = np.zeros((int(info[0]), 8), np.uint32)
+    ranks = np.zeros(face.size // 10, np.int32)
     rc = lib.b200rt_repack_probe(_ptr(vp_), vp_.size, _ptr(vn_), vn_.size, _ptr(face), face.size, int(n_materials),
-                                 _ptr(bvh_), bvh_.size, _ptr(nodes), nodes.size, _ptr(info))
+                                 _ptr(bvh_), bvh_.size, _ptr(nodes), nodes.size, _ptr(ranks), _ptr(info))
     if rc != 0:
         raise B200RTError(f"b200rt_repack_probe failed ({rc})")
     d = dict(n_inner=int(info[0]), node_f4=int(info[1]), depth=int(info[2]), ref_stack_need=int(info[3]),
              canonical=bool(info[4]), fast_ok=bool(info[5]), cmax=float(info[6]), cull_abs=float(info[7]),
              grid_base=info[8:11].copy(), grid_pitch=info[11:14].copy(), root_fc=info[14:17].copy(),
-             root_hq=info[17:20].copy(), ms_tris=float(info[20]), ms_walk=float(info[21]), ms_nodes=float(info[22]))
+             root_hq=info[17:20].copy(), ranks=ranks, ms_tris=float(info[20]), ms_walk=float(info[21]), ms_nodes=float(info[22]))
     return nodes, d
 
 

@@ -305,10 +305,6 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
       if (stack.size() > max_stack) max_stack = stack.size();
     }
   }
-  if (nonfinite) {
-    *err = "scene contains a non-finite coordinate (vertex or box plane)";
-    return B200RT_ERR_INVALID;
-  }
   // leaves per sub-tree: children come after their parent in the pre-order, so the reverse order is bottom-up
   R.leaf_count.assign((size_t)n_nodes, 0);
   for (size_t q = preorder.size(); q-- > 0;) {
@@ -318,6 +314,10 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
     R.leaf_count[cur] = ((int)rec[8] != -1 ? 1 : 0) + (l != -1 ? R.leaf_count[l] : 0) + (r != -1 ? R.leaf_count[r] : 0);
   }
   }  // !id_ordered
+  if (nonfinite) {
+    *err = "scene contains a non-finite coordinate (vertex or box plane)";
+    return B200RT_ERR_INVALID;
+  }
   R.depth = depth;
   R.ref_stack_need = (int)max_stack;
   if (R.ref_stack_need > kRefStackMax) canonical = false;  // closest_hit_nodrop's thread-local stack
@@ -447,7 +447,7 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
 
 extern "C" int b200rt_repack_probe(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const int32_t *face,
                                    int64_t n_face, int64_t n_materials, const float *bvh, int64_t n_bvh,
-                                   uint32_t *nodes_out, int64_t n_nodes_out, float *info) {
+                                   uint32_t *nodes_out, int64_t n_nodes_out, int32_t *rank_out, float *info) {
   if (!vp || !vn || !face || !bvh || !info || n_vp <= 0 || n_vp % 3 || n_vn <= 0 || n_vn % 3 || n_face <= 0 || n_face % 10 ||
       n_bvh <= 0 || n_bvh % 9 || n_materials <= 0)
     return B200RT_ERR_INVALID;
@@ -461,6 +461,8 @@ extern "C" int b200rt_repack_probe(const float *vp, int64_t n_vp, const float *v
     info[8 + k] = R.grid_base[k]; info[11 + k] = R.grid_pitch[k]; info[14 + k] = R.root_fc[k]; info[17 + k] = R.root_hq[k];
   }
   info[20] = (float)R.ms_tris; info[21] = (float)R.ms_walk; info[22] = (float)R.ms_nodes; info[23] = 0.0f;
+  if (rank_out)
+    for (int t = 0; t < R.n_tris; ++t) memcpy(&rank_out[t], &R.tris[3 * (size_t)t + 2].z, 4);
   if (nodes_out) {
     if (n_nodes_out < (int64_t)R.n_inner * 8) return B200RT_ERR_INVALID;
     for (int q = 0; q < R.n_inner; ++q) {

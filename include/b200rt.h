@@ -221,10 +221,12 @@ int b200rt_multi_get_stats(const b200rt_multi *m, b200rt_stats *stats);
  * scene") to nodes_out (capacity in uint32 words; may be NULL to query).  info_out (24 floats): [0] interior nodes,
  * [1] 16-byte units per node, [2] tree depth, [3] stack entries the reference-order walk needs, [4] canonical (fast
  * traversal applies), [5] fast_ok, [6] cmax, [7] cull_abs, [8..10] grid base, [11..13] grid pitch, [14..16] root fc,
- * [17..19] root hq, [20..22] host milliseconds of the three stages (triangles, tree walk, node records).  Lets the CPU test-suite check that every quantised box encloses the exact one. */
+ * [17..19] root hq, [20..22] host milliseconds of the three stages (triangles, tree walk, node records).  rank_out (one
+ * int32 per triangle, may be NULL): the triangle's position in the reference's visiting order, which breaks distance
+ * ties.  Lets the CPU test-suite check that every quantised box encloses the exact one. */
 int b200rt_repack_probe(const float *vertex_p, int64_t n_vertex_p, const float *vertex_n, int64_t n_vertex_n,
                         const int32_t *face_data, int64_t n_face_data, int64_t n_materials, const float *bvh,
-                        int64_t n_bvh, uint32_t *nodes_out, int64_t n_nodes_out, float *info_out);
+                        int64_t n_bvh, uint32_t *nodes_out, int64_t n_nodes_out, int32_t *rank_out, float *info_out);
 
 const char *b200rt_version(void);
 

@@ -312,7 +312,7 @@ def test_config5_scale_band_against_oracle_and_stack_cap_difference(gpu_ctx):
     assert np.array_equal(bits(got20[3 * i0:3 * i1]), bits(want20[3 * i0:3 * i1]))
     # ... and how far it is from the complete walk
     px = (got20[3 * i0:3 * i1].reshape(-1, 3) != a.reshape(-1, 3)).any(axis=1)
-    print(f"\\nconfig 5 band: stack need {need}, depth {depth}; pixels that differ between the reference's 20-entry stack and the "
+    print(f"\nconfig 5 band: stack need {need}, depth {depth}; pixels that differ between the reference's 20-entry stack and the "
           f"complete walk: {px.mean():.4%} of {px.size}")
     assert px.mean() < 0.5
 

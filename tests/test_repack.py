@@ -1,0 +1,168 @@
+"""Host half of b200rt_set_scene (csrc/scene_repack.cpp) through its GPU-free probe: the 32-byte node records must
+decode to boxes that ENCLOSE the exact float32 boxes of BVH.py's array (they only cull — but a box that is too small
+would silently drop geometry), the tree facts (depth, stack need, visiting ranks) must not depend on which of the two
+code paths derived them, and malformed input must be rejected wherever it sits in the arrays."""
+import numpy as np
+import pytest
+
+from ensem3a_openclraytracer_b200 import _capi
+from ensem3a_openclraytracer_b200._capi import B200RTError
+from tests import fixtures
+
+
+def probe(sc, bvh=None):
+    return _capi.repack_probe(sc["V_p"], sc["V_n"], sc["faceData"], max(1, len(sc["materialData"]) // 6),
+                              sc["BVH"] if bvh is None else bvh)
+
+
+def decode(nodes, info):
+    """(centre, half) float64 arrays [n_inner, 2 children, 3 axes] from the packed records (rt_trace.cuh)."""
+    w = nodes.astype(np.uint64)
+    hi, lo = (lambda x: x >> 16), (lambda x: x & 0xffff)
+    q = np.stack([np.stack([hi(w[:, 0]), lo(w[:, 0]), hi(w[:, 1])], 1), np.stack([lo(w[:, 1]), hi(w[:, 2]), lo(w[:, 2])], 1)], 1)
+    assert q.max() <= 32767
+    fbits = lambda x: x.astype(np.uint32).view(np.float32).astype(np.float64)
+    hq = np.stack([np.stack([fbits(w[:, 3] & 0xffff0000), fbits((w[:, 3] << 16) & 0xffffffff), fbits(w[:, 4] & 0xffff0000)], 1),
+                   np.stack([fbits((w[:, 4] << 16) & 0xffffffff), fbits(w[:, 5] & 0xffff0000), fbits((w[:, 5] << 16) & 0xffffffff)], 1)], 1)
+    base, pitch = info["grid_base"].astype(np.float64), info["grid_pitch"].astype(np.float64)
+    return base + (0.5 + q.astype(np.float64) / 65536.0) * pitch, hq * pitch
+
+
+def walk_pairs(sc_bvh, nodes, info):
+    """yields (record index, bvh9 node) for every interior node by following the refs from the root"""
+    bvh = sc_bvh.reshape(-1, 9)
+    nf4 = info["node_f4"]
+    refs = nodes[:, 6:8].astype(np.int64)
+    refs = np.where(refs >= 1 << 31, refs - (1 << 32), refs)
+    out, stack = [], [(0, 0)]
+    while stack:
+        rec, node = stack.pop()
+        out.append((rec, node))
+        for side in (0, 1):
+            ch = int(bvh[node, side])
+            ref = int(refs[rec, side])
+            if bvh[ch, 8] != -1:
+                assert ref == ~int(bvh[ch, 8])
+            else:
+                assert ref >= 0 and ref % nf4 == 0
+                stack.append((ref // nf4, ch))
+    return out
+
+
+@pytest.mark.parametrize("name", ["cornell", "monkey", "furnace", "serre", "proto", "single", "height_field"])
+def test_quantised_boxes_enclose_the_exact_ones(name):
+    if name == "height_field":
+        import ensem3a_openclraytracer_b200 as rt
+        from tests.synthetic import height_field_scene
+        sc = height_field_scene(64, seed=3)
+        sc["BVH"] = rt.build_bvh(sc["faceData"], sc["V_p"])
+    else:
+        sc = fixtures.load_scene(name)
+    nodes, info = probe(sc)
+    assert info["canonical"] and info["fast_ok"]
+    bvh = sc["BVH"].reshape(-1, 9).astype(np.float64)
+    n_tris = sc["faceData"].size // 10
+    if n_tris == 1:
+        assert info["n_inner"] == 0
+        return
+    assert info["n_inner"] == n_tris - 1
+    c, h = decode(nodes, info)
+    pairs = walk_pairs(sc["BVH"], nodes, info)
+    assert len(pairs) == info["n_inner"]
+    rec = np.array([p[0] for p in pairs])
+    node = np.array([p[1] for p in pairs])
+    worst = 0.0
+    for side in (0, 1):
+        ch = bvh[node, side].astype(int)
+        mn, mx = bvh[ch, 2:5], bvh[ch, 5:8]
+        lo, hi = c[rec, side] - h[rec, side], c[rec, side] + h[rec, side]
+        tol = 1e-12 * (np.abs(mn) + np.abs(mx) + 1.0)          # binary64 evaluation of the test itself
+        assert (lo <= mn + tol).all() and (hi >= mx - tol).all()
+        worst = max(worst, float(((hi - lo) - (mx - mn)).max() / info["grid_pitch"].max()))
+    assert worst < 2.0 ** -6                                    # never looser than bf16 rounding of a scene-sized box
+    # the root box in record units encloses node 0
+    rc = info["grid_base"].astype(np.float64) + info["root_fc"].astype(np.float64) * info["grid_pitch"]
+    rh = info["root_hq"].astype(np.float64) * info["grid_pitch"]
+    assert (rc - rh <= bvh[0, 2:5] + 1e-12).all() and (rc + rh >= bvh[0, 5:8] - 1e-12).all()
+    assert info["cmax"] >= np.abs(bvh[:, 2:8]).max()
+
+
+def renumber(bvh9):
+    """the same tree with children numbered BELOW their parents (root stays 0): forces the general serial walk"""
+    b = bvh9.reshape(-1, 9)
+    n = b.shape[0]
+    new_id = np.arange(n)
+    new_id[1:] = n - np.arange(1, n)
+    out = np.empty_like(b)
+    for old in range(n):
+        r = b[old].copy()
+        for k in (0, 1):
+            if r[k] != -1:
+                r[k] = new_id[int(r[k])]
+        out[new_id[old]] = r
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("name", ["cornell", "proto", "furnace"])
+def test_id_ordered_fast_path_equals_the_general_walk(name):
+    sc = fixtures.load_scene(name)
+    nodes_a, a = probe(sc)
+    nodes_b, b = probe(sc, renumber(sc["BVH"]))
+    for key in ("n_inner", "node_f4", "depth", "ref_stack_need", "canonical", "fast_ok", "cmax", "cull_abs"):
+        assert a[key] == b[key], key
+    assert np.array_equal(a["ranks"], b["ranks"])
+    assert np.array_equal(nodes_a, nodes_b)              # same pre-order over sibling pairs, same quantisation
+    assert sorted(a["ranks"]) == list(range(sc["faceData"].size // 10))
+
+
+def test_tree_facts_match_the_survey():
+    """max tree depth / max stack of the reference walk for the shipped scenes."""
+    for name, depth, need in (("cornell", 7, 5), ("monkey", 18, 14), ("furnace", 13, 13), ("serre", 18, 14)):
+        _, info = probe(fixtures.load_scene(name))
+        assert (info["depth"], info["ref_stack_need"]) == (depth, need), name
+
+
+def test_malformed_input_is_rejected_wherever_it_sits():
+    sc = fixtures.load_scene("proto")
+    n_nodes = sc["BVH"].size // 9
+    for key, bad in (("V_p", np.nan), ("V_p", np.inf), ("BVH", np.nan), ("BVH", -np.inf)):
+        arr = sc[key].copy()
+        if key == "V_p":
+            arr[3 * int(sc["faceData"][10 * (sc["faceData"].size // 20) + 8]) + 1] = bad     # a vertex some triangle uses
+        else:
+            arr[9 * (n_nodes // 2) + 4] = bad
+        broken = dict(sc)
+        broken[key] = arr
+        with pytest.raises(B200RTError):
+            probe(broken)
+    for mutate in ("cycle", "shared_child", "child_out_of_range", "tri_out_of_range", "face_index"):
+        broken = dict(sc)
+        bvh = sc["BVH"].copy()
+        if mutate == "cycle":
+            bvh[9 * 5] = 0.0                                     # node 5's left child is the root
+        elif mutate == "shared_child":
+            bvh[9 * 0 + 1] = bvh[9 * 0]                          # both children of the root are the same node
+        elif mutate == "child_out_of_range":
+            bvh[9 * 3 + 1] = float(n_nodes + 7)
+        elif mutate == "tri_out_of_range":
+            leaf = int(np.nonzero(bvh.reshape(-1, 9)[:, 8] != -1)[0][3])
+            bvh[9 * leaf + 8] = float(sc["faceData"].size)
+        else:
+            face = sc["faceData"].copy()
+            face[10 * 11 + 9] = -4
+            broken["faceData"] = face
+        broken["BVH"] = bvh
+        with pytest.raises(B200RTError):
+            probe(broken)
+
+
+def test_non_canonical_trees_are_flagged_not_rejected():
+    """A node that keeps a triangle AND children, or a child box poking out of its parent: legal for the reference's walk,
+    so accepted — but only the reference-order traversal may be used (canonical = False)."""
+    sc = fixtures.load_scene("proto")
+    bvh = sc["BVH"].copy().reshape(-1, 9)
+    inner = int(np.nonzero(bvh[:, 8] == -1)[0][4])
+    child = int(bvh[inner, 0])
+    bvh[child, 5] += 1.0                                         # child's max.x beyond the parent's
+    _, info = probe(sc, bvh.reshape(-1))
+    assert not info["canonical"]
