@@ -57,6 +57,7 @@ struct b200rt_ctx {
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
   int quorum = 20, refill_min = 8, tri_quorum = 4;
   int max_trace_ctas = 0;  // B200RT_MAX_TRACE_CTAS: cap on resident k_trace CTAs per SM (0 = what fits)
+  int compact_every = 8;   // B200RT_COMPACT_EVERY: wavefront iterations between two compactions of the path list
   std::vector<int32_t> tri_mat;  // for re-validating material edits
 
   // environment map
@@ -69,6 +70,7 @@ struct b200rt_ctx {
   // per-frame
   DevBuf d_prim_dirk, d_prim_tri, d_out, d_misc, d_tmp_a, d_tmp_b;
   DevBuf d_pA, d_pB, d_pC, d_pHit, d_list0, d_list1, d_cnt;  // wavefront path state (rt_kernels.cuh)
+  DevBuf d_slots, d_part_count;                               // order-preserving list compaction
   DeviceCounters *d_counters = nullptr;
 
   b200rt_stats stats;
@@ -224,7 +226,10 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   A->list[0] = static_cast<int *>(c->d_list0.p);
   A->list[1] = static_cast<int *>(c->d_list1.p);
   A->cnt = static_cast<unsigned int *>(c->d_cnt.p);
+  A->slots = static_cast<int *>(c->d_slots.p);
+  A->part_count = static_cast<unsigned int *>(c->d_part_count.p);
   A->wc = nullptr;
+  A->compact_every = c->compact_every;
   A->counters = c->d_counters;
   A->n_nodes = c->n_inner;
   A->n_tris = c->n_tris;
@@ -444,6 +449,8 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   if (ensure(c, c->d_pHit, npix * sizeof(int2))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_list0, npix * sizeof(int))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_list1, npix * sizeof(int))) return B200RT_ERR_CUDA;
+  const size_t n_work = (size_t)((width + 7) / 8) * ((height + 3) / 4) * 32;   // tile-ordered work items of k_primary
+  if (ensure(c, c->d_slots, n_work * sizeof(int))) return B200RT_ERR_CUDA;
   const size_t n_cnt = (size_t)n_iter + 2;             // cnt[0 .. n_iter + 1]
   const size_t cnt_bytes = (n_cnt + (size_t)n_iter + 1) * sizeof(unsigned int);  // then wc[0 .. n_iter]
   if (ensure(c, c->d_cnt, cnt_bytes)) return B200RT_ERR_CUDA;
@@ -456,6 +463,9 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   WaveLaunch wl;
   rc = prepare_wave(c, trav, smem, o.collect_stats != 0, &wl);
   if (rc) return rc;
+  if (ensure(c, c->d_part_count, (size_t)wl.shade_grid * sizeof(unsigned int))) return B200RT_ERR_CUDA;
+  A.part_count = static_cast<unsigned int *>(c->d_part_count.p);
+  A.slots = static_cast<int *>(c->d_slots.p);
   c->stats.kernel_launches = 0;
   c->stats.scene_in_smem = smem ? 1 : 0;
   CU(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
@@ -463,6 +473,10 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   CU(cudaEventRecord(c->ev[0], c->stream));
   rc = launch_primary(c, A, trav, smem, false, o.collect_stats != 0, nullptr, nullptr);
   if (rc) return rc;
+  // the first path list: k_primary's live pixels in tile order
+  k_count_parts<<<wl.shade_grid, kCompactBlock, 0, c->stream>>>(A.slots, (unsigned)A.n_work, A.part_count);
+  k_compact<<<wl.shade_grid, kCompactBlock, 0, c->stream>>>(A.slots, nullptr, (unsigned)A.n_work, A.part_count, A.list[0], A.cnt);
+  CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->kev_used = 0;
   if (o.time_kernels) {
@@ -473,14 +487,21 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
       c->kev.push_back(e);
     }
   }
+  int n_compactions = 0;
   for (int it = 0; it <= n_iter; ++it) {
     if (o.time_kernels) CU(cudaEventRecord(c->kev[c->kev_used++], c->stream));
     k_shade<<<wl.shade_grid, kShadeBlock, 0, c->stream>>>(A, it);
+    if (it < n_iter && (it + 1) % A.compact_every == 0) {  // close the gaps the finished pixels left, order kept (timed with k_shade)
+      k_compact<<<wl.shade_grid, kCompactBlock, 0, c->stream>>>(A.slots, A.cnt + it, 0u, A.part_count, A.list[(it + 1) & 1], A.cnt + it + 1);
+      ++n_compactions;
+    }
     if (o.time_kernels) CU(cudaEventRecord(c->kev[c->kev_used++], c->stream));
     if (it < n_iter) wl.trace<<<wl.trace_grid, kBlock, wl.trace_smem, c->stream>>>(A, it);
   }
   CU(cudaGetLastError());
-  c->stats.kernel_launches += 2 * n_iter + 1;
+  // k_count_parts + k_compact for the first list; k_shade + k_trace per iteration; the compactions; the closing k_shade
+  c->stats.kernel_launches += 2 + 2 * n_iter + n_compactions + 1;
+  c->stats.wave_iterations = n_iter;
   CU(cudaEventRecord(c->ev[2], c->stream));
   c->stats_pending = true;
   return 0;
@@ -545,6 +566,7 @@ int b200rt_create(int device, b200rt_ctx **out) {
   env_int("B200RT_REFILL_MIN", 1, 32, &c->refill_min);
   env_int("B200RT_TRI_QUORUM", 1, 32, &c->tri_quorum);
   env_int("B200RT_MAX_TRACE_CTAS", 1, 32, &c->max_trace_ctas);
+  env_int("B200RT_COMPACT_EVERY", 1, 1 << 20, &c->compact_every);
   auto bail = [&](const char *what, cudaError_t err) {
     fail(nullptr, B200RT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
     delete c;
@@ -566,7 +588,7 @@ void b200rt_destroy(b200rt_ctx *c) {
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_frames, &c->d_mats, &c->d_bvh9, &c->d_leafcnt, &c->d_prim_dirk,
                     &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b, &c->d_pA, &c->d_pB, &c->d_pC,
-                    &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt};
+                    &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt, &c->d_slots, &c->d_part_count};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->ibl_tex) cudaDestroyTextureObject(c->ibl_tex);

@@ -43,7 +43,11 @@ struct KernelArgs {
   float *out;             // width*height*3: running sums, then the image
   float4 *pA, *pB, *pC;
   int2 *pHit;
-  int *list[2];           // live paths, ping-pong
+  int *list[2];           // live paths, ping-pong, ALWAYS in the order of the frame's 8x4-pixel tiles; -1 = a path that
+                          // left the wavefront since the last compaction (k_shade and k_trace skip such entries)
+  int *slots;             // k_primary's / k_shade's output on the iterations that are followed by a compaction
+  unsigned int *part_count;  // survivors per contiguous part of `slots` (one part per producer CTA)
+  int compact_every;      // k_shade(i) hands its output to k_compact when (i + 1) % compact_every == 0
   unsigned int *cnt;      // cnt[i] = entries of the list consumed by shade iteration i
   unsigned int *wc;       // wc[i]  = rays of trace iteration i handed out so far
   DeviceCounters *counters;
@@ -195,16 +199,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
         }
       }
     }
-    if (!PARITY) {
-      const unsigned int m = __ballot_sync(0xffffffffu, live);
-      if (m != 0u) {
-        unsigned int base = 0;
-        const int leader = __ffs(m) - 1;
-        if ((int)lane == leader) base = atomicAdd(A.cnt, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (live) A.list[0][base + __popc(m & ((1u << lane) - 1u))] = i;
-      }
-    }
+    if (!PARITY) A.slots[w] = live ? i : -1;   // work items are in tile order; k_count_parts + k_compact make the first list
   }
   // one atomic per warp
   for (int o = 16; o > 0; o >>= 1) {
@@ -221,6 +216,80 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
   }
 }
 
+// ---- order-preserving list compaction -------------------------------------------------------------------------------
+// entries per producer CTA: the same function on both sides of the hand-over (a multiple of the block size, so that
+// warps read whole 128-byte lines)
+RT_HD unsigned int part_size(unsigned int n, unsigned int parts) {
+  const unsigned int per = (n + parts - 1u) / parts;
+  return (per + 127u) & ~127u;
+}
+
+constexpr int kCompactBlock = 128;
+
+// survivors per part of `slots` when the producer did not count them itself (k_primary's strided loop)
+__global__ void __launch_bounds__(kCompactBlock) k_count_parts(const int *__restrict__ slots, unsigned int n,
+                                                                unsigned int *__restrict__ part_count) {
+  const unsigned int part = part_size(n, gridDim.x);
+  const unsigned int end = min(n, (blockIdx.x + 1u) * part);
+  unsigned int c = 0;
+  for (unsigned int t = blockIdx.x * part + threadIdx.x; t < end; t += kCompactBlock) c += slots[t] >= 0 ? 1u : 0u;
+  __shared__ unsigned int total;
+  if (threadIdx.x == 0) total = 0u;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
+  __syncthreads();
+  if (threadIdx.x == 0) part_count[blockIdx.x] = total;
+}
+
+// list_out = the non-negative entries of slots[0 .. n), order kept; *n_out = their number.  One CTA per part (same
+// grid as the producer); its base is the sum of the earlier parts' counts.  n is read from n_src when given.
+__global__ void __launch_bounds__(kCompactBlock) k_compact(const int *__restrict__ slots, const unsigned int *n_src, unsigned int n_value,
+                                                            const unsigned int *__restrict__ part_count, int *__restrict__ list_out,
+                                                            unsigned int *__restrict__ n_out) {
+  const unsigned int n = n_src ? *n_src : n_value;
+  const unsigned int part = part_size(n, gridDim.x);
+  __shared__ unsigned int s_base, s_warp[kCompactBlock / 32];
+  const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  // sum of the earlier parts (and, in the last CTA, of all parts: the length of the new list)
+  unsigned int before = 0, all = 0;
+  for (unsigned int p = threadIdx.x; p < gridDim.x; p += kCompactBlock) {
+    const unsigned int c = part_count[p];
+    all += c;
+    if (p < blockIdx.x) before += c;
+  }
+  if (threadIdx.x == 0) s_base = 0u;
+  if (threadIdx.x < kCompactBlock / 32) s_warp[threadIdx.x] = 0u;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) {
+    before += __shfl_down_sync(0xffffffffu, before, o);
+    all += __shfl_down_sync(0xffffffffu, all, o);
+  }
+  if (lane == 0) {
+    if (before) atomicAdd(&s_base, before);
+    if (all) atomicAdd(&s_warp[0], all);
+  }
+  __syncthreads();
+  unsigned int base = s_base;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = s_warp[0];
+  __syncthreads();
+  const unsigned int end = min(n, (blockIdx.x + 1u) * part);
+  for (unsigned int t0 = blockIdx.x * part; t0 < end; t0 += kCompactBlock) {
+    const unsigned int t = t0 + threadIdx.x;
+    const int v = t < end ? slots[t] : -1;
+    const unsigned int m = __ballot_sync(0xffffffffu, v >= 0);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    unsigned int off = base;
+    for (unsigned int w = 0; w < warp; ++w) off += s_warp[w];
+    if (v >= 0) list_out[off + __popc(m & ((1u << lane) - 1u))] = v;
+    unsigned int step = 0;
+    for (unsigned int w = 0; w < kCompactBlock / 32; ++w) step += s_warp[w];
+    base += step;
+    __syncthreads();
+  }
+}
+
 // ---- shading ----------------------------------------------------------------------------------------------------
 // The per-path state machine is written as a sequence of phases with the warp re-converged between them, so that
 // e.g. the direction sampling runs once per warp for every lane that needs it, whichever way the lane got there
@@ -230,17 +299,27 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
   const SceneView &S = A.S;
   const unsigned int n_in = A.cnt[iter];
   const int *list_in = A.list[iter & 1];
-  int *list_out = A.list[(iter + 1) & 1];
-  unsigned int *n_out = A.cnt + iter + 1;
   const unsigned int lane = threadIdx.x & 31u;
   unsigned long long samples = 0;
-  unsigned int reval = 0, exact = 0;
-  const unsigned int warps = (gridDim.x * kShadeBlock) >> 5;
-  for (unsigned int tb = ((blockIdx.x * kShadeBlock + threadIdx.x) >> 5) << 5; tb < n_in; tb += warps << 5) {
+  unsigned int reval = 0, exact = 0, survivors = 0;
+  // Every CTA shades one contiguous part of the list and leaves, entry for entry, the path or -1 in the next list;
+  // every compact_every iterations k_compact closes the gaps without changing the order (paths leave the wavefront
+  // only when their pixel is finished, so gaps accumulate slowly).  The list therefore stays sorted by tile for the whole
+  // frame: the 32 paths of a warp — here and in k_trace — belong to neighbouring pixels, so the rays that restart
+  // from the cached primary hits leave from neighbouring points.  (An atomically appended list is a random
+  // permutation of the pixels after a few hundred iterations; on the 5 M-triangle scene that cost a third of the
+  // traversal speed.)
+  const bool compacting = ((iter + 1) % A.compact_every) == 0;
+  int *out = compacting ? A.slots : A.list[(iter + 1) & 1];
+  const unsigned int part = part_size(n_in, gridDim.x);
+  const unsigned int part_end = min(n_in, (blockIdx.x + 1u) * part);
+  for (unsigned int tb = blockIdx.x * part + (threadIdx.x & ~31u); tb < part_end; tb += kShadeBlock) {
     const unsigned int t = tb + lane;
-    const bool valid = t < n_in;
+    const bool in_part = t < part_end;
     // ---- phase 0: load -------------------------------------------------------------------------------------------
-    int pix = 0;
+    int pix = in_part ? list_in[t] : -1;
+    const bool valid = pix >= 0;   // -1: past the part's end, or a path that left the wavefront since the last compaction
+    if (!valid) pix = 0;
     uint32_t meta = 1u;
     rng_state g;
     g.a = 0u;
@@ -248,7 +327,6 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     float hk = 0.0f;
     int htri = -1;
     if (valid) {
-      pix = list_in[t];
       const float4 sb = A.pB[pix];
       meta = __float_as_uint(sb.z);
       g.a = __float_as_uint(sb.w);
@@ -394,14 +472,19 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
       A.pB[pix] = make_float4(d.y, d.z, __uint_as_float(meta_pack(0, sun_ray, seg_type, j, s)), __uint_as_float(g.a));
       A.pC[pix] = make_float4(acc.x, acc.y, acc.z, 0.0f);
     }
-    const unsigned int m = __ballot_sync(0xffffffffu, alive);
-    if (m != 0u) {
-      unsigned int base = 0;
-      const int leader = __ffs(m) - 1;
-      if ((int)lane == leader) base = atomicAdd(n_out, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (alive) list_out[base + __popc(m & ((1u << lane) - 1u))] = pix;
-    }
+    if (in_part) out[t] = alive ? pix : -1;
+    survivors += alive ? 1u : 0u;
+  }
+  if (!compacting) {  // the next list has this one's length
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.cnt[iter + 1] = n_in;
+  } else {  // survivors of this CTA's part, for k_compact
+    __shared__ unsigned int cta_survivors;
+    if (threadIdx.x == 0) cta_survivors = 0u;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) survivors += __shfl_down_sync(0xffffffffu, survivors, o);
+    if (lane == 0 && survivors) atomicAdd(&cta_survivors, survivors);
+    __syncthreads();
+    if (threadIdx.x == 0) A.part_count[blockIdx.x] = cta_survivors;
   }
   for (int o = 16; o > 0; o >>= 1) {
     samples += __shfl_down_sync(0xffffffffu, samples, o);
@@ -510,24 +593,26 @@ __global__ void __launch_bounds__(kBlock, B200RT_TRACE_MINB) k_trace(const __gri
         if (want && rank < take) {
           want = false;
           path = list[c_next + rank];
-          const float4 sa = A.pA[path], sb = A.pB[path];
-          const v3 o = mk3(sa.x, sa.y, sa.z);
-          const v3 d = ((__float_as_uint(sb.z) >> 3) & 1u) ? A.F.sun_dir : mk3(sa.w, sb.x, sb.y);
-          rays++;
-          if (TRAV == 0) {
-            if (ray_is_fast(S, o)) {
-              trav_begin<SMEM, STATS>(S, T, o, d, pn, parks, &tc);
-            } else {
-              // the margins of the conservative test are not proven for this origin / scene (|coordinate| > 2^40):
-              // k_shade's validation phase walks the ray exactly (closest_hit_nodrop), which keeps that walk's
-              // registers and local stack out of this kernel
-              T.best.tri = kHitNeedsExactWalk;
-              T.best.k = 1000.0f;
+          if (path >= 0) {   // -1: the path left the wavefront since the last compaction; the lane waits for the next refill
+            const float4 sa = A.pA[path], sb = A.pB[path];
+            const v3 o = mk3(sa.x, sa.y, sa.z);
+            const v3 d = ((__float_as_uint(sb.z) >> 3) & 1u) ? A.F.sun_dir : mk3(sa.w, sb.x, sb.y);
+            rays++;
+            if (TRAV == 0) {
+              if (ray_is_fast(S, o)) {
+                trav_begin<SMEM, STATS>(S, T, o, d, pn, parks, &tc);
+              } else {
+                // the margins of the conservative test are not proven for this origin / scene (|coordinate| > 2^40):
+                // k_shade's validation phase walks the ray exactly (closest_hit_nodrop), which keeps that walk's
+                // registers and local stack out of this kernel
+                T.best.tri = kHitNeedsExactWalk;
+                T.best.k = 1000.0f;
+                T.cur = -1;
+              }
+            } else {  // reference / verify traversal: whole walk at once
+              T.best = closest_hit<TRAV, SMEM, STATS>(S, o, d, st, parks, kBlock, &tc, &mism);
               T.cur = -1;
             }
-          } else {  // reference / verify traversal: whole walk at once
-            T.best = closest_hit<TRAV, SMEM, STATS>(S, o, d, st, parks, kBlock, &tc, &mism);
-            T.cur = -1;
           }
         }
         rank -= take;

@@ -85,7 +85,8 @@ typedef struct {
                              pushes (stack.cl:21-26) and only B200RT_TRAVERSAL_REFERENCE reproduces that */
   int32_t exact_walks;    /* wavefront rays with a zero / denormal / huge direction component, which skip the conservative
                              traversal and are walked exactly by the shading kernel */
-  int32_t reserved0;
+  int32_t wave_iterations; /* wavefront iterations of the last render = k_trace launches (kernel_launches also counts the
+                              shading, list-compaction and primary-hit kernels) */
 } b200rt_stats;
 
 void b200rt_default_opts(b200rt_opts *opts);
