@@ -13,4 +13,4 @@ if [ "$N" != "1" ]; then
   python tools/multi_handle_run.py $N monkey_cfg2:1920:1080:256 cornell:1920:1080:256 serre:3840:2160:64 > $O/multi_handle_g$N.jsonl 2> $O/multi_handle_g$N.err
 fi
 tail -c 600 $O/*_g$N.json $O/*_g$N.jsonl $O/*_g$N.log 2>/dev/null
-grep -l . $O/*_g$N.err 2>/dev/null | xargs -r tail -3
+grep -l . $O/*_g$N.err 2>/dev/null | xargs -r -n1 tail -n 3
