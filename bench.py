@@ -276,7 +276,7 @@ def main():
     npix = W * H
 
     kl = rt.KernelLauncher(None, None, None, None, cuda_device=local)  # the reference-facing plugin object
-    kl.rng_mode, kl.seed = rt.RNG_PHILOX, SEED
+    kl.rng_mode, kl.seed, kl.sample_streams = rt.RNG_PHILOX, SEED, -1
     kl.deep_trees = "nodrop"     # the measured configuration is the fast traversal on every tree (config 5 is deeper than
     #                              the reference's 20-entry stack; its default would switch to the reference-order walk)
     ctx = kl._ctx
@@ -288,7 +288,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     out_dev = torch.zeros(npix * 3, dtype=torch.float32, device=dev)
     dr = DistributedRenderer(ctx, rank, world, reduce=args.reduce) if world > 1 else None
-    philox = dict(rng_mode=rt.RNG_PHILOX, seed=SEED)
+    philox = dict(rng_mode=rt.RNG_PHILOX, seed=SEED, sample_streams=-1)       # the timed configuration
+    philox1 = dict(rng_mode=rt.RNG_PHILOX, seed=SEED, sample_streams=1)       # kernels timed / counted on their own
 
     def barrier():
         if world > 1:
@@ -326,7 +327,7 @@ def main():
 
     # ---- box / triangle tests per ray of the production traversal (FAST), counted on the GPU over 2 spp -----------
     o = rt.make_opts(traversal=rt.TRAVERSAL_FAST, collect_stats=True, output=rt.OUT_SUMS, sample_begin=0,
-                     sample_end=min(2, spp), **philox)
+                     sample_end=min(2, spp), **philox1)
     ctx.render_device(cam, env, W, H, spp, mb, out_dev.data_ptr(), o)
     st = ctx.stats()
     box_per_ray, tri_per_ray = st["box_tests"] / st["rays"], st["tri_tests"] / st["rays"]
@@ -337,16 +338,17 @@ def main():
         sampler.start()
     ms_per_step, rays_all_ranks, launches_step = timed(lambda: render_resident(cam, env, W, H, spp), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    streams_used = ctx.stats()["sample_streams"]
     rays_step = rays_all_ranks - (world - 1) * npix
     mrays = rays_step / ms_per_step / 1e3
 
     # ---- one profiled step: CUDA events around every k_shade / k_trace launch (roofline of the dominant kernel) -----
     if dr is None:
-        ctx.render_device(cam, env, W, H, spp, mb, out_dev.data_ptr(), rt.make_opts(time_kernels=True, **philox))
+        ctx.render_device(cam, env, W, H, spp, mb, out_dev.data_ptr(), rt.make_opts(time_kernels=True, **philox1))
     else:
         s0, s1 = split_range(spp, world)[rank]
         ctx.render_device(cam, env, W, H, spp, mb, out_dev.data_ptr(),
-                          rt.make_opts(time_kernels=True, output=rt.OUT_SUMS, sample_begin=s0, sample_end=s1, **philox))
+                          rt.make_opts(time_kernels=True, output=rt.OUT_SUMS, sample_begin=s0, sample_end=s1, **philox1))
     barrier()
     stp = ctx.stats()
 
@@ -358,7 +360,7 @@ def main():
         barrier()
         if rank == 0:
             multi = img.cpu().numpy()
-            ctx.render_device(cam, env, W, H, pspp, mb, out_dev.data_ptr(), rt.make_opts(**philox))
+            ctx.render_device(cam, env, W, H, pspp, mb, out_dev.data_ptr(), rt.make_opts(**philox1))
             torch.cuda.synchronize()
             single = out_dev.cpu().numpy()
             rel = np.abs(multi - single) / np.maximum(np.abs(single), 1e-3)
@@ -472,6 +474,7 @@ def main():
         "impl_config": {"rng": "philox4x32-10 keyed (pixel,sample,bounce)", "traversal": "fast",
                         "pipeline": "k_primary, then (spp*(maxBounce+2)) x (k_shade, k_trace) wavefront iterations",
                         "partition": "sample ranges" if world > 1 else "single GPU",
+                        "sample_streams": streams_used,
                         "reduce": args.reduce if world > 1 else None,
                         "l2": "256 MiB flush write between timed iterations", "scene_in_smem": bool(stp["scene_in_smem"]),
                         "triangles": scene_stats["triangles"], "bvh_depth": scene_stats["bvh_depth"],

@@ -55,6 +55,7 @@ class KernelLauncher(object):
         self.stack_cap = 20          # the reference's stack capacity (MathLib.cl:248); used by the reference-order walk
         self.deep_trees = "reference"  # "reference": trees needing > stack_cap entries are walked like the reference
         #                                 walks them (drops included); "nodrop": keep the fast, complete traversal
+        self.sample_streams = 0      # RNG_PHILOX only: -1 automatic, N > 1 concurrent sample ranges on each GPU (b200rt.h)
         self.collect_stats = False
         self.last_stats = None
         self._warned_deep = False
@@ -95,7 +96,7 @@ class KernelLauncher(object):
                               RuntimeWarning, stacklevel=2)
                 self._warned_deep = True
         opts = _capi.make_opts(rng_mode=self.rng_mode, traversal=traversal, stack_cap=self.stack_cap,
-                               seed=self.seed, collect_stats=self.collect_stats)
+                               seed=self.seed, collect_stats=self.collect_stats, sample_streams=self.sample_streams)
         out = h_img_out.reshape(-1)[:imgDim * 3]
         self._ctx.render(cam[:10], h_envData, width, height, int(spp), int(maxBounce), out=out, opts=opts)
         self.last_stats = self._ctx.stats()

@@ -27,7 +27,7 @@ class Opts(ctypes.Structure):
                 ("output", ctypes.c_int32), ("sample_begin", ctypes.c_int32), ("sample_end", ctypes.c_int32),
                 ("pixel_begin", ctypes.c_int32), ("pixel_end", ctypes.c_int32), ("seed", ctypes.c_uint64),
                 ("collect_stats", ctypes.c_int32), ("time_kernels", ctypes.c_int32), ("tile_row_mod", ctypes.c_int32),
-                ("tile_row_rem", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2)]
+                ("tile_row_rem", ctypes.c_int32), ("sample_streams", ctypes.c_int32), ("reserved", ctypes.c_int32 * 1)]
 
 
 class Stats(ctypes.Structure):
@@ -37,7 +37,8 @@ class Stats(ctypes.Structure):
                 ("kernel_launches", ctypes.c_int32), ("nodes", ctypes.c_int32), ("triangles", ctypes.c_int32),
                 ("bvh_depth", ctypes.c_int32), ("scene_in_smem", ctypes.c_int32), ("revalidated", ctypes.c_int32),
                 ("shade_kernel_ms", ctypes.c_float), ("trace_kernel_ms", ctypes.c_float), ("repack_ms", ctypes.c_float),
-                ("ref_stack_need", ctypes.c_int32), ("exact_walks", ctypes.c_int32), ("wave_iterations", ctypes.c_int32)]
+                ("ref_stack_need", ctypes.c_int32), ("exact_walks", ctypes.c_int32), ("wave_iterations", ctypes.c_int32),
+                ("sample_streams", ctypes.c_int32), ("primary_rays", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
@@ -145,7 +146,7 @@ def _i32(a):
 
 def make_opts(rng_mode=RNG_REFERENCE, traversal=TRAVERSAL_FAST, stack_cap=20, output=OUT_FINAL, sample_begin=0,
               sample_end=0, pixel_begin=0, pixel_end=0, seed=0, collect_stats=False, time_kernels=False, tile_row_mod=0,
-              tile_row_rem=0):
+              tile_row_rem=0, sample_streams=0):
     o = Opts()
     o.rng_mode, o.traversal, o.stack_cap, o.output = rng_mode, traversal, stack_cap, output
     o.sample_begin, o.sample_end, o.pixel_begin, o.pixel_end = sample_begin, sample_end, pixel_begin, pixel_end
@@ -153,6 +154,7 @@ def make_opts(rng_mode=RNG_REFERENCE, traversal=TRAVERSAL_FAST, stack_cap=20, ou
     o.collect_stats = 1 if collect_stats else 0
     o.time_kernels = 1 if time_kernels else 0
     o.tile_row_mod, o.tile_row_rem = int(tile_row_mod), int(tile_row_rem)
+    o.sample_streams = int(sample_streams)
     return o
 
 

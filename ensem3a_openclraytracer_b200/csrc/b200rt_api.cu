@@ -26,6 +26,7 @@ thread_local std::string g_create_error;
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  bool borrowed = false;  // a helper context's view of its parent's scene buffer: never freed or resized here
 };
 
 }  // namespace
@@ -75,6 +76,15 @@ struct b200rt_ctx {
 
   b200rt_stats stats;
   bool stats_pending = false;  // async render enqueued; counters/events not read yet
+
+  // sample streams (b200rt_opts.sample_streams): helper contexts on the same GPU, each with its own stream and path
+  // state, that borrow this context's scene and environment
+  std::vector<b200rt_ctx *> helpers;
+  bool is_helper = false;
+  uint64_t scene_epoch = 1, shared_epoch = 0;   // helpers re-borrow when the parent's scene / materials / map changed
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
+  DevBuf d_part;               // this context's own partial sums when the frame is cut into streams
+  int streams_used = 1;        // of the last render
 };
 
 namespace {
@@ -104,6 +114,7 @@ namespace {
 
 int ensure(b200rt_ctx *c, DevBuf &b, size_t bytes) {
   if (bytes == 0) bytes = 16;
+  if (b.borrowed) return fail(c, B200RT_ERR_INVALID, "internal: resize of a borrowed scene buffer");
   if (b.cap >= bytes) return 0;
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
@@ -363,11 +374,13 @@ int launch_trace_t(b200rt_ctx *c, const KernelArgs &A, const float *rays, long l
   return 0;
 }
 
-int read_counters(b200rt_ctx *c) {
+int read_counters_one(b200rt_ctx *c) {
   DeviceCounters h;
+  CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   c->stats.rays = h.rays;
+  c->stats.primary_rays = h.primary_rays;
   c->stats.box_tests = h.box_tests;
   c->stats.tri_tests = h.tri_tests;
   c->stats.mismatches = h.mismatches;
@@ -385,6 +398,36 @@ int read_counters(b200rt_ctx *c) {
       ((i & 1) ? c->stats.trace_kernel_ms : c->stats.shade_kernel_ms) += ms;
   c->kev_used = 0;
   c->stats_pending = false;
+  return 0;
+}
+
+// Counters and timings of the last render.  A frame cut into sample streams sums the work of its helper contexts
+// (the primary rays, which every stream traces for itself, count once) and is timed from the fork to the reduce.
+int read_counters(b200rt_ctx *c) {
+  int rc = read_counters_one(c);
+  if (rc || c->streams_used <= 1) return rc;
+  for (int k = 1; k < c->streams_used; ++k) {
+    b200rt_ctx *h = c->helpers[(size_t)k - 1];
+    rc = read_counters_one(h);
+    if (rc) return fail(c, rc, "sample stream %d: %s", k, h->err.c_str());
+    c->stats.rays += h->stats.rays - h->stats.primary_rays;
+    c->stats.box_tests += h->stats.box_tests;
+    c->stats.tri_tests += h->stats.tri_tests;
+    c->stats.mismatches += h->stats.mismatches;
+    c->stats.samples += h->stats.samples;
+    c->stats.revalidated += h->stats.revalidated;
+    c->stats.exact_walks += h->stats.exact_walks;
+    c->stats.kernel_launches += h->stats.kernel_launches;
+    c->stats.shade_kernel_ms += h->stats.shade_kernel_ms;   // kernels of different streams overlap: these are sums of
+    c->stats.trace_kernel_ms += h->stats.trace_kernel_ms;   // durations, not a partition of total_ms
+    c->stats.primary_ms = std::max(c->stats.primary_ms, h->stats.primary_ms);
+  }
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, c->ev_fork, c->ev_done) == cudaSuccess) {
+    c->stats.total_ms = ms;
+    c->stats.trace_ms = ms - c->stats.primary_ms;
+  }
+  c->stats.kernel_launches += 1;  // the reduce
   return 0;
 }
 
@@ -429,6 +472,7 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
                 const b200rt_opts *opts, float *d_out) {
   b200rt_opts o;
   if (opts) o = *opts; else b200rt_default_opts(&o);
+  c->streams_used = 1;
   int rc = check_frame_args(c, cam, width, height, spp, max_bounce, o, true, env);
   if (rc) return rc;
   if (!c->have_ibl) return fail(c, B200RT_ERR_NO_SCENE, "no environment map: call b200rt_set_ibl first");
@@ -467,6 +511,7 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   A.part_count = static_cast<unsigned int *>(c->d_part_count.p);
   A.slots = static_cast<int *>(c->d_slots.p);
   c->stats.kernel_launches = 0;
+  c->stats.sample_streams = 1;
   c->stats.scene_in_smem = smem ? 1 : 0;
   CU(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
   CU(cudaMemsetAsync(c->d_cnt.p, 0, cnt_bytes, c->stream));
@@ -503,6 +548,126 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   c->stats.kernel_launches += 2 + 2 * n_iter + n_compactions + 1;
   c->stats.wave_iterations = n_iter;
   CU(cudaEventRecord(c->ev[2], c->stream));
+  c->stats_pending = true;
+  return 0;
+}
+
+// ---- sample streams ------------------------------------------------------------------------------------------------
+// One path per pixel is in flight inside a render (a pixel's samples run in order).  With the counter-based
+// generator a frame's sample range can be cut into N contiguous parts that do not depend on each other; each part is
+// an ordinary render into its own partial-sum buffer, issued on its own CUDA stream by a helper context that borrows
+// this context's scene, and one k_reduce_finalize on this context's stream adds the parts in order.  The GPU then
+// holds N samples of a pixel at once: small frames fill it, and on large frames one part's shading overlaps another
+// part's tracing (the two kernels are bound by different units).
+void borrow_scene(b200rt_ctx *p, b200rt_ctx *h) {
+  auto lend = [](DevBuf &dst, const DevBuf &src) { dst.p = src.p; dst.cap = src.cap; dst.borrowed = true; };
+  lend(h->d_nodes, p->d_nodes); lend(h->d_tris, p->d_tris); lend(h->d_normals, p->d_normals); lend(h->d_tboxes, p->d_tboxes);
+  lend(h->d_frames, p->d_frames); lend(h->d_mats, p->d_mats); lend(h->d_bvh9, p->d_bvh9); lend(h->d_leafcnt, p->d_leafcnt);
+  h->n_nodes9 = p->n_nodes9; h->n_inner = p->n_inner; h->n_tris = p->n_tris; h->n_mats = p->n_mats;
+  h->node_f4 = p->node_f4; h->depth = p->depth; h->ref_stack_need = p->ref_stack_need; h->canonical = p->canonical;
+  h->root_ref = p->root_ref;
+  for (int k = 0; k < 3; ++k) {
+    h->grid_base[k] = p->grid_base[k]; h->grid_pitch[k] = p->grid_pitch[k];
+    h->root_fc[k] = p->root_fc[k]; h->root_hq[k] = p->root_hq[k];
+  }
+  h->cull_abs = p->cull_abs; h->cmax = p->cmax; h->fast_ok = p->fast_ok;
+  h->quorum = p->quorum; h->refill_min = p->refill_min; h->tri_quorum = p->tri_quorum;
+  h->max_trace_ctas = p->max_trace_ctas; h->compact_every = p->compact_every;
+  h->have_scene = p->have_scene;
+  h->ibl_tex = p->ibl_tex; h->ibl_w = p->ibl_w; h->ibl_h = p->ibl_h; h->have_ibl = p->have_ibl;
+  h->shared_epoch = p->scene_epoch;
+}
+
+int resolve_streams(const b200rt_opts &o, int width, int height, int s0, int s1) {
+  if (o.rng_mode != B200RT_RNG_PHILOX) return 1;   // the reference generator is one serial stream per pixel
+  int n = o.sample_streams;
+  if (n < 0) {
+    const long long npix = (long long)width * height;
+    n = npix >= 1000000 ? 2 : (npix >= 200000 ? 4 : 8);
+  }
+  if (n > 16) n = 16;
+  if (n > s1 - s0) n = s1 - s0;
+  return n < 1 ? 1 : n;
+}
+
+int render_frame(b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp, int max_bounce,
+                 const b200rt_opts *opts, float *d_out) {
+  b200rt_opts o;
+  if (opts) o = *opts; else b200rt_default_opts(&o);
+  if (o.sample_streams < -1 || o.sample_streams > 16)
+    return fail(c, B200RT_ERR_INVALID, "bad sample_streams %d (-1 automatic, 0 / 1 off, up to 16)", o.sample_streams);
+  int s0 = o.sample_begin, s1 = o.sample_end;
+  if (s1 <= 0) { s0 = 0; s1 = spp; }
+  const int n = (width > 0 && height > 0 && spp > 0) ? resolve_streams(o, width, height, s0, s1) : 1;
+  if (n <= 1 || c->is_helper) return render_impl(c, cam, env, width, height, spp, max_bounce, &o, d_out);
+  int rc = check_frame_args(c, cam, width, height, spp, max_bounce, o, true, env);
+  if (rc) return rc;
+  if (!c->have_ibl) return fail(c, B200RT_ERR_NO_SCENE, "no environment map: call b200rt_set_ibl first");
+  CU(cudaSetDevice(c->device));
+  while ((int)c->helpers.size() < n - 1) {
+    b200rt_ctx *h = nullptr;
+    rc = b200rt_create(c->device, &h);
+    if (rc) return fail(c, rc, "sample stream context: %s", b200rt_last_error(nullptr));
+    h->is_helper = true;
+    c->helpers.push_back(h);
+  }
+  if (!c->ev_fork) {
+    CU(cudaEventCreate(&c->ev_fork));
+    CU(cudaEventCreate(&c->ev_done));
+  }
+  const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+  if (ensure(c, c->d_part, bytes)) return B200RT_ERR_CUDA;
+  CU(cudaEventRecord(c->ev_fork, c->stream));   // the parts start after whatever the caller enqueued before this frame
+  std::vector<int> rcs((size_t)n, 0);
+  const int total = s1 - s0, base = total / n, extra = total % n;
+#pragma omp parallel for num_threads(n) schedule(static, 1)
+  for (int k = 0; k < n; ++k) {
+    b200rt_ctx *h = k == 0 ? c : c->helpers[(size_t)k - 1];
+    b200rt_opts ok = o;
+    ok.sample_streams = 1;
+    ok.output = B200RT_OUT_SUMS;
+    ok.sample_begin = s0 + k * base + (k < extra ? k : extra);
+    ok.sample_end = ok.sample_begin + base + (k < extra ? 1 : 0);
+    int r = 0;
+    if (cudaSetDevice(c->device) != cudaSuccess) r = B200RT_ERR_CUDA;
+    float *part = nullptr;
+    if (!r && k > 0) {
+      if (h->shared_epoch != c->scene_epoch) borrow_scene(c, h);
+      if (!h->ev_join && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) r = B200RT_ERR_CUDA;
+      if (!r && cudaStreamWaitEvent(h->stream, c->ev_fork, 0) != cudaSuccess) r = B200RT_ERR_CUDA;
+      if (!r) r = ensure(h, h->d_part, bytes);
+      part = static_cast<float *>(h->d_part.p);
+    } else if (!r) {
+      part = static_cast<float *>(c->d_part.p);
+    }
+    if (!r && cudaMemsetAsync(part, 0, bytes, h->stream) != cudaSuccess) r = B200RT_ERR_CUDA;
+    if (!r) r = render_impl(h, cam, env, width, height, spp, max_bounce, &ok, part);
+    if (!r && k > 0 && cudaEventRecord(h->ev_join, h->stream) != cudaSuccess) r = B200RT_ERR_CUDA;
+    if (r == B200RT_ERR_CUDA && h->err.empty()) h->err = "CUDA call failed while enqueueing a sample stream";
+    rcs[(size_t)k] = r;
+  }
+  for (int k = 0; k < n; ++k)
+    if (rcs[(size_t)k]) {
+      b200rt_ctx *h = k == 0 ? c : c->helpers[(size_t)k - 1];
+      const std::string msg = h->err;
+      return fail(c, rcs[(size_t)k], "sample stream %d: %s", k, msg.c_str());
+    }
+  // join on this context's stream, add the parts in order; a whole frame is finalised, a partial range stays sums
+  PartList pl;
+  pl.n = n;
+  pl.p[0] = static_cast<const float *>(c->d_part.p);
+  for (int k = 1; k < n; ++k) {
+    CU(cudaStreamWaitEvent(c->stream, c->helpers[(size_t)k - 1]->ev_join, 0));
+    pl.p[k] = static_cast<const float *>(c->helpers[(size_t)k - 1]->d_part.p);
+  }
+  const long long nn = (long long)width * height * 3;
+  const bool aligned = (reinterpret_cast<uintptr_t>(d_out) % 16) == 0;
+  const int grid = (int)std::min<long long>((nn / 4 + 255) / 256 + 1, (long long)c->sm_count * 8);
+  k_reduce_finalize<<<grid, 256, 0, c->stream>>>(pl, d_out, aligned ? nn / 4 : 0, nn, o.output == B200RT_OUT_FINAL ? (float)spp : 0.0f);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev_done, c->stream));
+  c->streams_used = n;
+  c->stats.sample_streams = n;
   c->stats_pending = true;
   return 0;
 }
@@ -586,11 +751,21 @@ void b200rt_destroy(b200rt_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (b200rt_ctx *h : c->helpers) b200rt_destroy(h);
+  c->helpers.clear();
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->d_part.p) cudaFree(c->d_part.p);
+  if (c->is_helper) {  // the environment map belongs to the parent
+    c->ibl_tex = 0;
+    c->ibl_array = nullptr;
+  }
   DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_frames, &c->d_mats, &c->d_bvh9, &c->d_leafcnt, &c->d_prim_dirk,
                     &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b, &c->d_pA, &c->d_pB, &c->d_pC,
                     &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt, &c->d_slots, &c->d_part_count};
   for (DevBuf *b : bufs)
-    if (b->p) cudaFree(b->p);
+    if (b->p && !b->borrowed) cudaFree(b->p);
   if (c->ibl_tex) cudaDestroyTextureObject(c->ibl_tex);
   if (c->ibl_array) cudaFreeArray(c->ibl_array);
   if (c->d_counters) cudaFree(c->d_counters);
@@ -620,6 +795,7 @@ int b200rt_set_materials(b200rt_ctx *c, const float *mat, int64_t n_mat) {
   CU(cudaStreamSynchronize(c->stream));
   c->n_mats = nm;
   c->mat_hash = h;
+  ++c->scene_epoch;
   return 0;
 }
 
@@ -711,6 +887,7 @@ int upload_scene(b200rt_ctx *c, const Repacked &R, const SceneArgs &a, uint64_t 
   c->have_scene = true;
   c->have_scene_cached = true;
   c->scene_hash = h;
+  ++c->scene_epoch;
   c->stats.repack_ms = (float)(R.ms_tris + R.ms_walk + R.ms_nodes);
   c->stats.ref_stack_need = c->ref_stack_need;
   c->stats.nodes = R.n_nodes9;
@@ -791,6 +968,7 @@ int b200rt_set_ibl(b200rt_ctx *c, const uint8_t *rgba, int width, int height) {
   c->ibl_w = width;
   c->ibl_h = height;
   c->ibl_hash = h;
+  ++c->scene_epoch;
   c->have_ibl = true;
   c->stats.upload_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return 0;
@@ -800,7 +978,7 @@ int b200rt_render_device(b200rt_ctx *c, const float *cam, const float *env, int 
                          int max_bounce, const b200rt_opts *opts, float *d_out) {
   if (!c) return B200RT_ERR_INVALID;
   if (!d_out) return fail(c, B200RT_ERR_INVALID, "d_out_rgb is NULL");
-  return render_impl(c, cam, env, width, height, spp, max_bounce, opts, d_out);
+  return render_frame(c, cam, env, width, height, spp, max_bounce, opts, d_out);
 }
 
 int b200rt_render(b200rt_ctx *c, const float *cam, const float *env, int width, int height, int spp, int max_bounce,
@@ -812,7 +990,7 @@ int b200rt_render(b200rt_ctx *c, const float *cam, const float *env, int width, 
   CU(cudaSetDevice(c->device));
   if (ensure(c, c->d_out, bytes)) return B200RT_ERR_CUDA;
   CU(cudaMemsetAsync(c->d_out.p, 0, bytes, c->stream));
-  int rc = render_impl(c, cam, env, width, height, spp, max_bounce, opts, static_cast<float *>(c->d_out.p));
+  int rc = render_frame(c, cam, env, width, height, spp, max_bounce, opts, static_cast<float *>(c->d_out.p));
   if (rc) return rc;
   CU(cudaMemcpyAsync(out, c->d_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));  // blocking read-back, KernelLauncher.py:78
   CU(cudaStreamSynchronize(c->stream));
@@ -830,7 +1008,7 @@ int b200rt_render_rgb8(b200rt_ctx *c, const float *cam, const float *env, int wi
   if (ensure(c, c->d_out, n * sizeof(float))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_tmp_a, n)) return B200RT_ERR_CUDA;
   CU(cudaMemsetAsync(c->d_out.p, 0, n * sizeof(float), c->stream));
-  int rc = render_impl(c, cam, env, width, height, spp, max_bounce, opts, static_cast<float *>(c->d_out.p));
+  int rc = render_frame(c, cam, env, width, height, spp, max_bounce, opts, static_cast<float *>(c->d_out.p));
   if (rc) return rc;
   int grid = (int)std::min<long long>(((long long)n + 255) / 256, (long long)c->sm_count * 16);
   k_quantize8<<<grid, 256, 0, c->stream>>>(static_cast<const float *>(c->d_out.p), static_cast<uint8_t *>(c->d_tmp_a.p), (long long)n);
@@ -1171,9 +1349,8 @@ int b200rt_multi_create(const int *devices, int n_devices, b200rt_multi **out) {
   if (!out) return mfail(nullptr, B200RT_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (!devices || n_devices < 1 || n_devices > 16) return mfail(nullptr, B200RT_ERR_INVALID, "1..16 devices expected (got %d)", n_devices);
-  for (int i = 0; i < n_devices; ++i)
-    for (int j = 0; j < i; ++j)
-      if (devices[i] == devices[j]) return mfail(nullptr, B200RT_ERR_INVALID, "device %d listed twice", devices[i]);
+  // A device may be listed several times: every entry gets its own context, buffers and stream, so a frame too small
+  // to fill one GPU (one path per pixel in flight) runs as several concurrent sample-range renders on it.
   m = new b200rt_multi();
   memset(&m->stats, 0, sizeof m->stats);
   m->ctx.assign((size_t)n_devices, nullptr);
@@ -1188,6 +1365,7 @@ int b200rt_multi_create(const int *devices, int n_devices, b200rt_multi **out) {
   }
   cudaSetDevice(devices[0]);
   for (int i = 1; i < n_devices; ++i) {
+    if (devices[i] == devices[0]) continue;  // the same GPU: plain loads
     int can = 0;
     cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
     if (can) {
@@ -1303,7 +1481,7 @@ int b200rt_multi_render(b200rt_multi *m, const float *cam, const float *env, int
     if (!rc && cudaMemsetAsync(c->d_out.p, 0, bytes, c->stream) != cudaSuccess) rc = B200RT_ERR_CUDA;
     const bool empty = (oi.sample_begin == oi.sample_end) || (oi.tile_row_mod > 1 && oi.tile_row_rem >= tile_rows);
     c->stats.rays = 0; c->stats.samples = 0; c->stats.total_ms = 0; c->stats.kernel_launches = 0;
-    if (!rc && !empty) rc = render_impl(c, cam, env, width, height, spp, max_bounce, &oi, static_cast<float *>(c->d_out.p));
+    if (!rc && !empty) rc = render_frame(c, cam, env, width, height, spp, max_bounce, &oi, static_cast<float *>(c->d_out.p));
     if (!rc && cudaEventRecord(m->done[i], c->stream) != cudaSuccess) rc = B200RT_ERR_CUDA;
     if (rc == B200RT_ERR_CUDA && c->err.empty()) c->err = "CUDA call failed while enqueueing the frame";
     rcs[i] = rc;

@@ -21,11 +21,11 @@ namespace b200rt {
 
 constexpr int kBlock = 128;        // k_primary, k_trace, k_trace_rays
 constexpr int kShadeBlock = 128;
-constexpr unsigned kChunk = 32;    // rays a warp claims from the list per atomic
+constexpr unsigned kChunk = 32;    // rays a warp claims from the list per atomic (64 / 128 lose to the longer tails)
 constexpr int kHitNeedsExactWalk = -2;  // pHit.x of a ray k_trace did not walk (see k_trace); k_shade walks it exactly
 
 struct DeviceCounters {
-  unsigned long long rays, box_tests, tri_tests, mismatches, samples, revalidated, exact_walks;
+  unsigned long long rays, box_tests, tri_tests, mismatches, samples, revalidated, exact_walks, primary_rays;
 };
 
 // path state, one entry per pixel:
@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
   }
   if (lane == 0) {
     if (rays) atomicAdd(&A.counters->rays, rays);
+    if (rays) atomicAdd(&A.counters->primary_rays, rays);
     if (mism) atomicAdd(&A.counters->mismatches, (unsigned long long)mism);
   }
   if (STATS) {
@@ -680,8 +681,10 @@ struct PartList {
   const float *p[16];
   int n;
 };
+// spp <= 0: plain sum (partial sums of a partial sample range stay partial sums)
 __global__ void k_reduce_finalize(const __grid_constant__ PartList parts, float *__restrict__ out, long long n4, long long n,
                                   float spp) {
+  const bool fin = spp > 0.0f;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long v = i; v < n4; v += stride) {
@@ -690,16 +693,18 @@ __global__ void k_reduce_finalize(const __grid_constant__ PartList parts, float 
       float4 b = reinterpret_cast<const float4 *>(parts.p[r])[v];
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    a.x = clamp01(a.x / spp);
-    a.y = clamp01(a.y / spp);
-    a.z = clamp01(a.z / spp);
-    a.w = clamp01(a.w / spp);
+    if (fin) {
+      a.x = clamp01(a.x / spp);
+      a.y = clamp01(a.y / spp);
+      a.z = clamp01(a.z / spp);
+      a.w = clamp01(a.w / spp);
+    }
     reinterpret_cast<float4 *>(out)[v] = a;
   }
   for (long long e = 4 * n4 + i; e < n; e += stride) {
     float a = parts.p[0][e];
     for (int r = 1; r < parts.n; ++r) a += parts.p[r][e];
-    out[e] = clamp01(a / spp);
+    out[e] = fin ? clamp01(a / spp) : a;
   }
 }
 

@@ -109,7 +109,7 @@ class DistributedRenderer:
 
     # ---- one frame -----------------------------------------------------------------------------------------
     def render(self, cam, env, width, height, spp, max_bounce, rng_mode=_capi.RNG_PHILOX, seed=0,
-               traversal=_capi.TRAVERSAL_FAST):
+               traversal=_capi.TRAVERSAL_FAST, sample_streams=0):
         """Enqueues the frame; returns rank 0's device tensor (width*height*3, final image) or None."""
         torch, dist = self.torch, self.dist
         n = width * height * 3
@@ -124,7 +124,8 @@ class DistributedRenderer:
             self._accum.zero_()
             if not empty:
                 opts = _capi.make_opts(rng_mode=rng_mode, traversal=traversal, output=_capi.OUT_SUMS, sample_begin=s0,
-                                       sample_end=s1, tile_row_mod=tmod, tile_row_rem=trem, seed=seed)
+                                       sample_end=s1, tile_row_mod=tmod, tile_row_rem=trem, seed=seed,
+                                       sample_streams=sample_streams)
                 self.ctx.render_device(cam, env, width, height, spp, max_bounce, self._accum.data_ptr(), opts)
         if self.reduce == "peer":
             dist.all_reduce(self._flag, group=self.group)       # every rank's partial sums are complete

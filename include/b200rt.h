@@ -59,7 +59,14 @@ typedef struct {
                             (stats.shade_kernel_ms / trace_kernel_ms); adds two event records per iteration */
   int32_t tile_row_mod;  /* > 1: of the frame's rows of 8x4-pixel tiles (4 pixel rows each) only those with        */
   int32_t tile_row_rem;  /*   tile_row % tile_row_mod == tile_row_rem are rendered (interleaved multi-GPU split)  */
-  int32_t reserved[2];
+  int32_t sample_streams; /* B200RT_RNG_PHILOX only.  0 or 1: one path per pixel in flight, samples accumulated one by one (bit-
+                             identical to the oracle's accumulation order).  N > 1: the sample range is cut into N contiguous
+                             parts that run concurrently on N CUDA streams of the same GPU (each with its own path state) and
+                             whose per-pixel sums are added in part order by the reduce kernel — several samples of a pixel in
+                             flight, which fills the GPU on small frames and overlaps shading with tracing on large ones.
+                             -1: chosen from the frame size (2 from 1 Mpixel, 4 from 0.2 Mpixel, else 8).  The image equals
+                             the one-stream image up to the order of N float additions per pixel. */
+  int32_t reserved[1];
 } b200rt_opts;
 
 typedef struct {
@@ -85,8 +92,10 @@ typedef struct {
                              pushes (stack.cl:21-26) and only B200RT_TRAVERSAL_REFERENCE reproduces that */
   int32_t exact_walks;    /* wavefront rays with a zero / denormal / huge direction component, which skip the conservative
                              traversal and are walked exactly by the shading kernel */
-  int32_t wave_iterations; /* wavefront iterations of the last render = k_trace launches (kernel_launches also counts the
-                              shading, list-compaction and primary-hit kernels) */
+  int32_t wave_iterations; /* wavefront iterations of the last render = k_trace launches per sample stream (kernel_launches
+                              also counts the shading, list-compaction and primary-hit kernels) */
+  int32_t sample_streams;  /* concurrent sample-range renders the last frame was cut into (b200rt_opts.sample_streams) */
+  uint64_t primary_rays;   /* rays of the primary-hit kernel; N sample streams trace them N times, `rays` counts them once */
 } b200rt_stats;
 
 void b200rt_default_opts(b200rt_opts *opts);

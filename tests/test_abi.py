@@ -41,7 +41,7 @@ def test_default_opts_and_struct_layout():
     assert (o.rng_mode, o.traversal, o.stack_cap, o.output) == (rt.RNG_REFERENCE, rt.TRAVERSAL_FAST, 20, rt.OUT_FINAL)
     assert (o.sample_begin, o.sample_end, o.pixel_begin, o.pixel_end, o.seed, o.collect_stats) == (0, 0, 0, 0, 0, 0)
     assert ctypes.sizeof(rt.Opts) == 64       # 8 x int32, uint64, 6 x int32
-    assert ctypes.sizeof(rt.Stats) == 104     # 5 x uint64, 4 x float, 6 x int32, 3 x float, 3 x int32
+    assert ctypes.sizeof(rt.Stats) == 120     # 5 x uint64, 4 x float, 6 x int32, 3 x float, 4 x int32, uint64
 
 
 def test_version_string():

@@ -524,3 +524,44 @@ def test_failed_scene_upload_does_not_poison_the_cached_one(gpu_ctx):
     fixtures.upload(gpu_ctx, shallow, ibl)
     after = gpu_ctx.render(cam, env, 64, 64, 3, 4)
     assert np.array_equal(bits(before), bits(after))
+
+
+@pytest.mark.parametrize("name,res", [("cornell", 96), ("monkey_cfg2", 80)])
+def test_sample_streams_sum_the_same_samples_in_part_order(gpu_ctx, name, res):
+    """b200rt_opts.sample_streams = N: the frame's samples are cut into N contiguous parts that render concurrently on one
+    GPU, and the parts' per-pixel sums are added in part order.  Same rays, same samples; the image is bit-for-bit what
+    the oracle gives when its per-part sums are added in that order (and equals the one-stream image within 1e-4)."""
+    sc, ibl = fixtures.load_scene(name), fixtures.load_ibl()
+    fixtures.upload(gpu_ctx, sc, ibl)
+    cam, env = fixtures.cam_env(sc["params"], res)
+    spp = 11
+    one = gpu_ctx.render(cam, env, res, res, spp, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=6))
+    s_one = gpu_ctx.stats()
+    for n in (2, 3, 8, -1):
+        got = gpu_ctx.render(cam, env, res, res, spp, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=6, sample_streams=n))
+        st = gpu_ctx.stats()
+        parts = st["sample_streams"]
+        assert parts == (n if n > 0 else 8)
+        assert (st["rays"], st["samples"]) == (s_one["rays"], s_one["samples"])
+        base, extra = divmod(spp, parts)
+        acc, s0 = None, 0
+        for k in range(parts):
+            s1 = s0 + base + (1 if k < extra else 0)
+            part, _ = oracle.render(sc, cam, env, res * res, spp, 4, ibl, rng_mode=oracle.RNG_PHILOX, seed=6, raw_sums=True, s0=s0, s1=s1)
+            acc = part if acc is None else (acc + part).astype(np.float32)
+            s0 = s1
+        q = acc / np.float32(spp)
+        want = np.where(np.isnan(q), np.float32(1.0), np.fmax(np.fmin(q, np.float32(1.0)), np.float32(0.0))).astype(np.float32)
+        assert np.array_equal(bits(got), bits(want))
+        rel = np.abs(got - one) / np.maximum(np.abs(one), REL_FLOOR)    # a different order of the float additions only
+        assert rel.max() <= REL_TOL
+    # a caller-side sample range stays raw sums; the reference generator ignores the option (its stream is serial)
+    a = gpu_ctx.render(cam, env, res, res, spp, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=6, output=rt.OUT_SUMS,
+                                                                   sample_begin=2, sample_end=9, sample_streams=3))
+    b = gpu_ctx.render(cam, env, res, res, spp, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=6, output=rt.OUT_SUMS,
+                                                                   sample_begin=2, sample_end=9))
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+    r1 = gpu_ctx.render(cam, env, res, res, 5, 4, opts=rt.make_opts(sample_streams=4))
+    assert gpu_ctx.stats()["sample_streams"] == 1
+    ref, _ = oracle.render(sc, cam, env, res * res, 5, 4, ibl)
+    assert np.array_equal(bits(r1), bits(ref))
