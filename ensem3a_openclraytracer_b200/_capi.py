@@ -16,6 +16,7 @@ CSRC = os.path.join(_PKG, "csrc")
 RNG_REFERENCE, RNG_PHILOX = 0, 1
 TRAVERSAL_FAST, TRAVERSAL_REFERENCE, TRAVERSAL_VERIFY = 0, 1, 2
 OUT_FINAL, OUT_SUMS = 0, 1
+SAMPLING_REFERENCE, SAMPLING_IMPORTANCE = 0, 1
 
 
 class B200RTError(RuntimeError):
@@ -27,7 +28,7 @@ class Opts(ctypes.Structure):
                 ("output", ctypes.c_int32), ("sample_begin", ctypes.c_int32), ("sample_end", ctypes.c_int32),
                 ("pixel_begin", ctypes.c_int32), ("pixel_end", ctypes.c_int32), ("seed", ctypes.c_uint64),
                 ("collect_stats", ctypes.c_int32), ("time_kernels", ctypes.c_int32), ("tile_row_mod", ctypes.c_int32),
-                ("tile_row_rem", ctypes.c_int32), ("sample_streams", ctypes.c_int32), ("reserved", ctypes.c_int32 * 1)]
+                ("tile_row_rem", ctypes.c_int32), ("sample_streams", ctypes.c_int32), ("sampling", ctypes.c_int32)]
 
 
 class Stats(ctypes.Structure):
@@ -146,7 +147,7 @@ def _i32(a):
 
 def make_opts(rng_mode=RNG_REFERENCE, traversal=TRAVERSAL_FAST, stack_cap=20, output=OUT_FINAL, sample_begin=0,
               sample_end=0, pixel_begin=0, pixel_end=0, seed=0, collect_stats=False, time_kernels=False, tile_row_mod=0,
-              tile_row_rem=0, sample_streams=0):
+              tile_row_rem=0, sample_streams=0, sampling=SAMPLING_REFERENCE):
     o = Opts()
     o.rng_mode, o.traversal, o.stack_cap, o.output = rng_mode, traversal, stack_cap, output
     o.sample_begin, o.sample_end, o.pixel_begin, o.pixel_end = sample_begin, sample_end, pixel_begin, pixel_end
@@ -155,6 +156,7 @@ def make_opts(rng_mode=RNG_REFERENCE, traversal=TRAVERSAL_FAST, stack_cap=20, ou
     o.time_kernels = 1 if time_kernels else 0
     o.tile_row_mod, o.tile_row_rem = int(tile_row_mod), int(tile_row_rem)
     o.sample_streams = int(sample_streams)
+    o.sampling = int(sampling)
     return o
 
 

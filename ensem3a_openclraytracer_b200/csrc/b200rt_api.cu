@@ -187,6 +187,7 @@ void frame_setup(const b200rt_ctx *c, const float *cam, const float *env, int wi
   F->rng_mode = o.rng_mode;
   F->key0 = (uint32_t)(o.seed & 0xffffffffull);
   F->key1 = (uint32_t)(o.seed >> 32);
+  F->sampling = o.sampling;
 }
 
 size_t scene_smem_bytes(const b200rt_ctx *c) { return (size_t)c->n_inner * 48 + (size_t)c->n_tris * 48; }
@@ -449,6 +450,8 @@ int check_frame_args(b200rt_ctx *c, const float *cam, int width, int height, int
   if (o.rng_mode != B200RT_RNG_REFERENCE && o.rng_mode != B200RT_RNG_PHILOX)
     return fail(c, B200RT_ERR_INVALID, "bad rng_mode %d", o.rng_mode);
   if (o.traversal < 0 || o.traversal > 2) return fail(c, B200RT_ERR_INVALID, "bad traversal %d", o.traversal);
+  if (o.sampling != B200RT_SAMPLING_REFERENCE && o.sampling != B200RT_SAMPLING_IMPORTANCE)
+    return fail(c, B200RT_ERR_INVALID, "bad sampling mode %d", o.sampling);
   if (o.output != B200RT_OUT_FINAL && o.output != B200RT_OUT_SUMS)
     return fail(c, B200RT_ERR_INVALID, "bad output mode %d", o.output);
   if (o.sample_end > 0) {

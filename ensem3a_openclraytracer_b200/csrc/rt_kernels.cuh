@@ -453,7 +453,8 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
           nd = sample_cosine(n, tf, u0, u1, &inv_pdf);
           brdf = m.color * (1.0f / 3.14f);
         } else {
-          nd = sample_uniform(n, tf, u0, u1, &inv_pdf);
+          if (F.sampling == 1) nd = sample_glossy_importance(m.roughness, tf.un, d, u0, u1, &inv_pdf);
+          else nd = sample_uniform(n, tf, u0, u1, &inv_pdf);
           brdf = bsdf_ggx(m, neg3(d), nd, n);
         }
       }

@@ -26,6 +26,7 @@ struct FrameParams {
   int out_mode;
   int rng_mode;
   uint32_t key0, key1;
+  int sampling;     // B200RT_SAMPLING_*
 };
 
 struct Material {
@@ -192,6 +193,72 @@ RT_DEV v3 bsdf_ggx(const Material &m, v3 v, v3 l, v3 n) {
   float kd = (1.0f - F) * (1.0f - 0.5f);
   v3 diffuse = (m.color * kd) / 3.14f;
   return mk3(diffuse.x + spec, diffuse.y + spec, diffuse.z + spec);
+}
+
+// ---- opt-in: importance sampling of glossy surfaces (oracle/rt_oracle.c sample_glossy_importance) -----
+// The reference draws the next direction of a glossy surface uniformly over the hemisphere and carries BRDF_GGX as a
+// weight (MathLib.cl:342-366, Raytracing.cl:63-66): at low roughness almost every sample misses the lobe.  This draws
+// from a one-sample mixture of (a) the GGX distribution of visible normals [Heitz 2018] with alpha = roughness — the
+// normal distribution BRDF_GGX itself uses (MathLib.cl:470-472) — reflected about the sampled normal, and (b) a
+// cosine-weighted lobe for the BRDF's diffuse term, and returns 1 / pdf of the mixture, so the caller's
+// BRDF_GGX * |cos| * inv_pdf is an estimator of the same integral.  u0 picks the lobe and is stretched back to [0, 1).
+// A view direction below the surface (the reference does not flip normals) uses the cosine lobe alone.
+// Statement order is mirrored by the oracle, so images stay bit-identical to it.
+RT_DEV v3 sample_glossy_importance(float roughness, v3 un, v3 d_in, float u0, float u1, float *inv_pdf) {
+  const float kPi = 3.14159265f, kTwoPi = 6.2831853f;
+  const v3 N = un;
+  const v3 Vw = unit(neg3(d_in));
+  const float ndv = dot(N, Vw);
+  // orthonormal basis around N (Duff et al. 2017)
+  const float sg = copysignf(1.0f, N.z);
+  const float a = -1.0f / (sg + N.z);
+  const float b = N.x * N.y * a;
+  const v3 T = mk3(1.0f + sg * N.x * N.x * a, sg * b, -sg * N.x);
+  const v3 B = mk3(b, sg + N.y * N.y * a, -N.y);
+  const bool spec = ndv > 0.0f && u0 < 0.5f;
+  const float u0r = u0 < 0.5f ? u0 * 2.0f : u0 * 2.0f - 1.0f;
+  const float al = roughness;
+  float sp, cp;
+  cr_sincos(kTwoPi * u1, &sp, &cp);
+  const float r = sqrtf(u0r);
+  v3 l;
+  if (spec) {
+    const v3 Vh = unit(mk3(al * dot(Vw, T), al * dot(Vw, B), ndv));
+    const float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+    v3 T1 = mk3(1.0f, 0.0f, 0.0f);
+    if (lensq > 0.0f) {
+      const float inv = 1.0f / sqrtf(lensq);
+      T1 = mk3(-Vh.y * inv, Vh.x * inv, 0.0f);
+    }
+    const v3 T2 = cross(Vh, T1);
+    const float t1 = r * cp;
+    float t2 = r * sp;
+    const float s = 0.5f * (1.0f + Vh.z);
+    t2 = (1.0f - s) * sqrtf(fmaxf(0.0f, 1.0f - t1 * t1)) + s * t2;
+    const float t3 = sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
+    const v3 Nh = ((T1 * t1) + (T2 * t2)) + (Vh * t3);
+    const v3 hl = unit(mk3(al * Nh.x, al * Nh.y, fmaxf(0.0f, Nh.z)));
+    const v3 h = ((T * hl.x) + (B * hl.y)) + (N * hl.z);
+    l = (h * (2.0f * dot(Vw, h))) - Vw;
+  } else {
+    l = ((T * (r * cp)) + (B * (r * sp))) + (N * sqrtf(fmaxf(0.0f, 1.0f - u0r)));
+  }
+  const float ndl = dot(N, l);
+  const float pdf_cos = fmaxf(ndl, 0.0f) / kPi;
+  float pdf_spec = 0.0f;
+  if (ndv > 0.0f && ndl > 0.0f) {
+    const v3 h = unit(l + Vw);
+    const float ndh = dot(N, h);
+    const float a2 = al * al;
+    const float dden = ndh * ndh * (a2 - 1.0f) + 1.0f;
+    const float D = a2 / (kPi * dden * dden);
+    const float G1 = (2.0f * ndv) / (ndv + sqrtf(a2 + (1.0f - a2) * ndv * ndv));
+    pdf_spec = (G1 * D) / (4.0f * ndv);
+  }
+  const float ps = ndv > 0.0f ? 0.5f : 0.0f;
+  const float pdf = ps * pdf_spec + (1.0f - ps) * pdf_cos;
+  *inv_pdf = pdf > 0.0f ? 1.0f / pdf : 0.0f;
+  return l;
 }
 
 }  // namespace b200rt

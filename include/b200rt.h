@@ -40,6 +40,13 @@ typedef enum {
 #define B200RT_TRAVERSAL_REFERENCE 1 /* the reference's visiting order incl. its capped stack (stack.cl:21-26) */
 #define B200RT_TRAVERSAL_VERIFY 2    /* runs both per ray, counts disagreements in stats.mismatches, keeps REFERENCE */
 
+/* direction sampling on glossy (type 2) surfaces — SURVEY.md 8f-4, opt-in, changes the image (same expectation) */
+#define B200RT_SAMPLING_REFERENCE 0  /* uniform hemisphere, the GGX BRDF as a weight (MathLib.cl:342-366, Raytracing.cl:63-66) */
+#define B200RT_SAMPLING_IMPORTANCE 1 /* one-sample mixture of GGX visible-normal sampling (the lobe the author's dead
+                                        rand_sample_GGX aims at, MathLib.cl:369-387) and cosine sampling of the BRDF's
+                                        diffuse term; the same BRDF_GGX * cos / pdf estimator, far less variance at low
+                                        roughness */
+
 /* output modes */
 #define B200RT_OUT_FINAL 0 /* mean over spp, clamped to [0,1]  (Raytracing.cl:211-219) */
 #define B200RT_OUT_SUMS 1  /* raw per-pixel sums over [sample_begin, sample_end) — multi-GPU partials */
@@ -66,7 +73,7 @@ typedef struct {
                              flight, which fills the GPU on small frames and overlaps shading with tracing on large ones.
                              -1: chosen from the frame size (2 from 1 Mpixel, 4 from 0.2 Mpixel, else 8).  The image equals
                              the one-stream image up to the order of N float additions per pixel. */
-  int32_t reserved[1];
+  int32_t sampling;       /* B200RT_SAMPLING_*: 0 the reference's estimator (default); 1 importance sampling of glossy surfaces */
 } b200rt_opts;
 
 typedef struct {

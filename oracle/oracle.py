@@ -19,7 +19,7 @@ _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 class OrcOpts(ctypes.Structure):
     _fields_ = [("rng_mode", ctypes.c_int), ("seed_lo", ctypes.c_uint32), ("seed_hi", ctypes.c_uint32),
                 ("stack_cap", ctypes.c_int), ("s0", ctypes.c_int), ("s1", ctypes.c_int),
-                ("raw_sums", ctypes.c_int), ("nthreads", ctypes.c_int)]
+                ("raw_sums", ctypes.c_int), ("nthreads", ctypes.c_int), ("sampling", ctypes.c_int)]
 
 
 def build(verbose=False):
@@ -63,7 +63,7 @@ RNG_PHILOX = 1
 
 
 def render(scene, cam, env, img_dim, spp, max_bounce, ibl_rgba, i0=0, i1=None, rng_mode=RNG_REFERENCE,
-           seed=0, stack_cap=20, s0=0, s1=0, raw_sums=False, nthreads=0):
+           seed=0, stack_cap=20, s0=0, s1=0, raw_sums=False, nthreads=0, sampling=0):
     """Returns (out[img_dim*3] float32, counters dict)."""
     lib = _lib()
     i1 = img_dim if i1 is None else i1
@@ -71,7 +71,7 @@ def render(scene, cam, env, img_dim, spp, max_bounce, ibl_rgba, i0=0, i1=None, r
     ibl = np.ascontiguousarray(ibl_rgba, dtype=np.uint8)
     h, w = ibl.shape[0], ibl.shape[1]
     opts = OrcOpts(rng_mode, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, stack_cap, s0, s1,
-                   1 if raw_sums else 0, nthreads)
+                   1 if raw_sums else 0, nthreads, sampling)
     cnt = (ctypes.c_ulonglong * 4)()
     face = scene["faceData"]
     lib.orc_render(out, scene["V_p"], scene["V_n"], scene["V_uv"], face, scene["materialData"], scene["BVH"],

@@ -76,6 +76,7 @@ typedef struct {
   int s0, s1;          /* sample range [s0,s1); s1 <= 0 means [0, spp) */
   int raw_sums;        /* 1: write the un-normalised, un-clamped sum over [s0,s1) */
   int nthreads;        /* 0 = OpenMP default */
+  int sampling;        /* 0 = the reference's estimator; 1 = importance sampling of glossy surfaces (opt-in) */
 } orc_opts;
 
 typedef struct {
@@ -86,6 +87,7 @@ typedef struct {
   int ibl_w, ibl_h;
   const float *cam, *env;
   int stack_cap;
+  int sampling;
 } scene_t;
 
 /* =========================================================================================
@@ -349,6 +351,69 @@ static v3 sample_uniform(v3 n, rng_t *g, float *inv_pdf) {
   return w;
 }
 
+/* Opt-in (orc_opts.sampling = 1; NOT the reference's estimator — the reference draws glossy directions uniformly,
+ * MathLib.cl:342-366): one-sample mixture of GGX visible-normal sampling [Heitz 2018] with alpha = roughness (the normal
+ * distribution of BRDF_GGX, MathLib.cl:470-472; the lobe the author's dead rand_sample_GGX aims at, :369-387) and a
+ * cosine lobe for the BRDF's diffuse term; returns the direction and 1 / pdf of the mixture.  Restated statement by
+ * statement from csrc/rt_shade.cuh::sample_glossy_importance so that the two agree bit for bit. */
+static v3 sample_glossy_importance(float roughness, v3 n, v3 d_in, rng_t *g, float *inv_pdf) {
+  const float kPi = 3.14159265f, kTwoPi = 6.2831853f;
+  float u0 = rng_next(g);
+  float u1 = rng_next(g);
+  v3 N = unit3(n);
+  v3 Vw = unit3(V(-d_in.x, -d_in.y, -d_in.z));
+  float ndv = dot3(N, Vw);
+  float sg = copysignf(1.0f, N.z);
+  float a = -1.0f / (sg + N.z);
+  float b = N.x * N.y * a;
+  v3 T = V(1.0f + sg * N.x * N.x * a, sg * b, -sg * N.x);
+  v3 B = V(b, sg + N.y * N.y * a, -N.y);
+  int spec = ndv > 0.0f && u0 < 0.5f;
+  float u0r = u0 < 0.5f ? u0 * 2.0f : u0 * 2.0f - 1.0f;
+  float al = roughness;
+  float phi = kTwoPi * u1;
+  float sp = cr_sin(phi), cp = cr_cos(phi);
+  float r = sqrtf(u0r);
+  v3 l;
+  if (spec) {
+    v3 Vh = unit3(V(al * dot3(Vw, T), al * dot3(Vw, B), ndv));
+    float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+    v3 T1 = V(1.0f, 0.0f, 0.0f);
+    if (lensq > 0.0f) {
+      float inv = 1.0f / sqrtf(lensq);
+      T1 = V(-Vh.y * inv, Vh.x * inv, 0.0f);
+    }
+    v3 T2 = cross3(Vh, T1);
+    float t1 = r * cp;
+    float t2 = r * sp;
+    float s = 0.5f * (1.0f + Vh.z);
+    t2 = (1.0f - s) * sqrtf(fmaxf(0.0f, 1.0f - t1 * t1)) + s * t2;
+    float t3 = sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
+    v3 Nh = add3(add3(scale3(T1, t1), scale3(T2, t2)), scale3(Vh, t3));
+    v3 hl = unit3(V(al * Nh.x, al * Nh.y, fmaxf(0.0f, Nh.z)));
+    v3 h = add3(add3(scale3(T, hl.x), scale3(B, hl.y)), scale3(N, hl.z));
+    l = sub3(scale3(h, 2.0f * dot3(Vw, h)), Vw);
+  } else {
+    l = add3(add3(scale3(T, r * cp), scale3(B, r * sp)), scale3(N, sqrtf(fmaxf(0.0f, 1.0f - u0r))));
+  }
+  float ndl = dot3(N, l);
+  float pdf_cos = fmaxf(ndl, 0.0f) / kPi;
+  float pdf_spec = 0.0f;
+  if (ndv > 0.0f && ndl > 0.0f) {
+    v3 h = unit3(add3(l, Vw));
+    float ndh = dot3(N, h);
+    float a2 = al * al;
+    float dden = ndh * ndh * (a2 - 1.0f) + 1.0f;
+    float D = a2 / (kPi * dden * dden);
+    float G1 = (2.0f * ndv) / (ndv + sqrtf(a2 + (1.0f - a2) * ndv * ndv));
+    pdf_spec = (G1 * D) / (4.0f * ndv);
+  }
+  float ps = ndv > 0.0f ? 0.5f : 0.0f;
+  float pdf = ps * pdf_spec + (1.0f - ps) * pdf_cos;
+  *inv_pdf = pdf > 0.0f ? 1.0f / pdf : 0.0f;
+  return l;
+}
+
 /* =========================================================================================
  * BSDFs — MathLib.cl:461-512
  * ======================================================================================= */
@@ -406,7 +471,8 @@ static v3 path_sample(const scene_t *sc, int max_bounce, hit_t H, ray_t R, mat_t
         brdf = scale3(M.color, 1.0f / 3.14f);
         break;
       case 2:
-        nb.d = sample_uniform(H.n, g, &inv_pdf);
+        if (sc->sampling == 1) nb.d = sample_glossy_importance(M.roughness, H.n, R.d, g, &inv_pdf);
+        else nb.d = sample_uniform(H.n, g, &inv_pdf);
         brdf = bsdf_ggx(&M, V(-R.d.x, -R.d.y, -R.d.z), nb.d, H.n);
         break;
       case 3:
@@ -453,6 +519,7 @@ static v3 path_sample(const scene_t *sc, int max_bounce, hit_t H, ray_t R, mat_t
 static void fill_scene(scene_t *sc, const float *vp, const float *vn, const float *vuv, const int *face,
                        const float *mat, const float *bvh, const float *cam, const float *env,
                        int tri_count, const unsigned char *ibl, int ibl_w, int ibl_h, int stack_cap) {
+  sc->sampling = 0;
   sc->vp = vp; sc->vn = vn; sc->vuv = vuv; sc->face = face; sc->mat = mat; sc->bvh = bvh;
   sc->cam = cam; sc->env = env; sc->tri_count = tri_count;
   sc->ibl = ibl; sc->ibl_w = ibl_w; sc->ibl_h = ibl_h;
@@ -467,6 +534,7 @@ void orc_render(float *out, const float *vp, const float *vn, const float *vuv, 
                 int i0, int i1, const orc_opts *opts, unsigned long long *counters_out) {
   scene_t sc;
   fill_scene(&sc, vp, vn, vuv, face, mat, bvh, cam, env, tri_count, ibl, ibl_w, ibl_h, opts->stack_cap);
+  sc.sampling = opts->sampling;
   int s0 = opts->s0, s1 = opts->s1;
   if (s1 <= 0) { s0 = 0; s1 = spp; }
   unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;

@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Variance at equal spp of the opt-in glossy importance sampling (b200rt_opts.sampling = 1) against the reference's
+uniform-hemisphere estimator, on fixture scenes: RMSE of an spp-sample image against a converged image of the SAME
+integrand (the mean of both estimators' long runs), per sampler.  One JSON line per scene.
+usage: variance_probe.py [spp=64] [converged_spp=8192] [scene:w:h:ibl ...]"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ensem3a_openclraytracer_b200 as rt  # noqa: E402
+from tests import fixtures  # noqa: E402
+
+
+def main():
+    a = sys.argv[1:]
+    spp = int(a[0]) if a else 64
+    big = int(a[1]) if len(a) > 1 else 8192
+    cases = a[2:] or ["monkey_cfg2:960:540:preview", "furnace_cfg3:512:512:grey", "serre:960:540:preview"]
+    ctx = rt.Context(0)
+    for c in cases:
+        name, w, h, ibl_name = c.split(":")
+        w, h = int(w), int(h)
+        sc, ibl = fixtures.load_scene(name), fixtures.load_ibl(ibl_name)
+        fixtures.upload(ctx, sc, ibl)
+        cam, env = fixtures.cam_env(sc["params"], w, h)
+
+        def sums(mode, seed, n):
+            o = rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=seed, sampling=mode, output=rt.OUT_SUMS, sample_streams=-1)
+            out = ctx.render(cam, env, w, h, n, 4, opts=o)
+            return out.astype(np.float64) / n, ctx.stats()
+
+        conv_ref, _ = sums(rt.SAMPLING_REFERENCE, 1000, big)
+        conv_imp, _ = sums(rt.SAMPLING_IMPORTANCE, 2000, big)
+        truth = 0.5 * (conv_ref + conv_imp)
+        line = dict(scene=name, width=w, height=h, spp=spp, converged_spp=big,
+                    converged_mean_reference=float(conv_ref.mean()), converged_mean_importance=float(conv_imp.mean()),
+                    rmse_between_converged_images=float(np.sqrt(np.mean((conv_ref - conv_imp) ** 2))))
+        for mode, key in ((rt.SAMPLING_REFERENCE, "reference"), (rt.SAMPLING_IMPORTANCE, "importance")):
+            errs, ms = [], []
+            for seed in range(4):
+                img, st = sums(mode, seed, spp)
+                errs.append(np.sqrt(np.mean((img - truth) ** 2)))
+                ms.append(st["total_ms"])
+            line[f"rmse_{key}"] = float(np.mean(errs))
+            line[f"device_ms_{key}"] = float(np.mean(ms))
+        line["rmse_ratio"] = line["rmse_reference"] / line["rmse_importance"]
+        line["equal_error_sample_ratio"] = line["rmse_ratio"] ** 2
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
