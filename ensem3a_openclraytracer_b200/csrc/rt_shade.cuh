@@ -195,7 +195,7 @@ RT_DEV v3 bsdf_ggx(const Material &m, v3 v, v3 l, v3 n) {
   return mk3(diffuse.x + spec, diffuse.y + spec, diffuse.z + spec);
 }
 
-// ---- opt-in: importance sampling of glossy surfaces (oracle/rt_oracle.c sample_glossy_importance) -----
+// ---- opt-in: importance sampling of glossy surfaces ------------------------------------------------------
 // The reference draws the next direction of a glossy surface uniformly over the hemisphere and carries BRDF_GGX as a
 // weight (MathLib.cl:342-366, Raytracing.cl:63-66): at low roughness almost every sample misses the lobe.  This draws
 // from a one-sample mixture of (a) the GGX distribution of visible normals [Heitz 2018] with alpha = roughness — the
@@ -203,7 +203,7 @@ RT_DEV v3 bsdf_ggx(const Material &m, v3 v, v3 l, v3 n) {
 // cosine-weighted lobe for the BRDF's diffuse term, and returns 1 / pdf of the mixture, so the caller's
 // BRDF_GGX * |cos| * inv_pdf is an estimator of the same integral.  u0 picks the lobe and is stretched back to [0, 1).
 // A view direction below the surface (the reference does not flip normals) uses the cosine lobe alone.
-// Statement order is mirrored by the oracle, so images stay bit-identical to it.
+// The test-side CPU restatement mirrors this statement order, so images stay bit-identical to it.
 RT_DEV v3 sample_glossy_importance(float roughness, v3 un, v3 d_in, float u0, float u1, float *inv_pdf) {
   const float kPi = 3.14159265f, kTwoPi = 6.2831853f;
   const v3 N = un;
