@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact(const int *__restrict
 // The per-path state machine is written as a sequence of phases with the warp re-converged between them, so that
 // e.g. the direction sampling runs once per warp for every lane that needs it, whichever way the lane got there
 // (bounce hit, or sample ended and the next one starts from the cached primary hit).
+// 8 CTAs per SM: the kernel is bound by the latency of its gathers; 5-7 (no spills) and 9-12 resident CTAs were all slower
 __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant__ KernelArgs A, int iter) {
   const FrameParams &F = A.F;
   const SceneView &S = A.S;
@@ -511,11 +512,8 @@ __global__ void k_tri_frames(const float4 *__restrict__ normals, int n_tris, flo
 }
 
 // ---- tracing ------------------------------------------------------------------------------------------------------
-#ifndef B200RT_TRACE_MINB
-#define B200RT_TRACE_MINB 1
-#endif
 template <int TRAV, bool SMEM, bool STATS>
-__global__ void __launch_bounds__(kBlock, B200RT_TRACE_MINB) k_trace(const __grid_constant__ KernelArgs A, int iter) {
+__global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ KernelArgs A, int iter) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned int n = A.cnt[iter + 1];
   if (n == 0u) return;
