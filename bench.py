@@ -14,7 +14,8 @@ frame once.  Scene buffers are the committed fixtures produced by the reference'
 value      Mrays/s, device time (CUDA events on the launching stream), inputs resident in HBM.
 e2e        the same metric through the reference-facing call (KernelLauncher.launch_Raytracing) with HOST buffers:
            every step re-uploads scene + environment (caches invalidated), renders, and reads the image back.
-roofline   dominant kernel = k_trace (one launch per wavefront iteration).  Configs 1-4 keep their scene in
+roofline   dominant kernel = k_trace (one launch per wavefront iteration; timed on its own in one extra step rendered
+           with a single sample stream, because the timed steps overlap two streams' kernels).  Configs 1-4 keep their scene in
            L1/L2/shared memory, so the bound is the SM ISSUE rate: achieved = thread-instructions/s
            = (40 per box test + 80 per triangle test, counted by the production FAST traversal itself in a
            collect_stats pass) x rays of the k_trace launches / summed duration of those launches (CUDA events around
@@ -462,6 +463,8 @@ def main():
         roofline = {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "Gthread-instr/s", "frac": achieved / peak,
                     "peak_source": f"{sm_count} SMs x 4 schedulers x 32 lanes x {sm_mhz:.0f} MHz",
                     "thread_instr_per_ray": instr_per_ray,
+                    # the same work over the whole timed step (shading, compaction, reduce and all sample streams included)
+                    "frac_of_whole_step": (rays_step - npix) / world * instr_per_ray / (ms_per_step * 1e-3) / 1e9 / peak,
                     "l2_bytes_per_ray_this_layout": bytes_per_ray,
                     "note": "scene is cache-resident (SURVEY 8d): the bound is the SM issue rate; algorithmic work = 40 "
                             "thread-instructions per box test + 80 per triangle test of the production (FAST) traversal"}
