@@ -16,7 +16,7 @@ CSRC = os.path.join(_PKG, "csrc")
 RNG_REFERENCE, RNG_PHILOX = 0, 1
 TRAVERSAL_FAST, TRAVERSAL_REFERENCE, TRAVERSAL_VERIFY = 0, 1, 2
 OUT_FINAL, OUT_SUMS = 0, 1
-SAMPLING_REFERENCE, SAMPLING_IMPORTANCE = 0, 1
+SAMPLING_REFERENCE, SAMPLING_IMPORTANCE, SAMPLING_LIGHTS = 0, 1, 2
 
 
 class B200RTError(RuntimeError):

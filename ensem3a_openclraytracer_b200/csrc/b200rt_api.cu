@@ -60,6 +60,9 @@ struct b200rt_ctx {
   int max_trace_ctas = 0;  // B200RT_MAX_TRACE_CTAS: cap on resident k_trace CTAs per SM (0 = what fits)
   int compact_every = 8;   // B200RT_COMPACT_EVERY: wavefront iterations between two compactions of the path list
   std::vector<int32_t> tri_mat;  // for re-validating material edits
+  DevBuf d_light;                // triangles whose material is emissive, ascending (opt-in light sampling)
+  int n_light = 0;
+  DevBuf d_pS, d_pL, d_pR;       // light sampling: three more float4 of path state
 
   // environment map
   bool have_ibl = false;
@@ -235,6 +238,11 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   A->pB = static_cast<float4 *>(c->d_pB.p);
   A->pC = static_cast<float4 *>(c->d_pC.p);
   A->pHit = static_cast<int2 *>(c->d_pHit.p);
+  A->light = static_cast<const int *>(c->d_light.p);
+  A->n_light = c->n_light;
+  A->pS = static_cast<float4 *>(c->d_pS.p);
+  A->pL = static_cast<float4 *>(c->d_pL.p);
+  A->pR = static_cast<float4 *>(c->d_pR.p);
   A->list[0] = static_cast<int *>(c->d_list0.p);
   A->list[1] = static_cast<int *>(c->d_list1.p);
   A->cnt = static_cast<unsigned int *>(c->d_cnt.p);
@@ -341,7 +349,7 @@ int prepare_trace_t(b200rt_ctx *c, WaveLaunch *w) {
 
 int prepare_wave(b200rt_ctx *c, int trav, bool smem, bool stats, WaveLaunch *w) {
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, kShadeBlock, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<false>, kShadeBlock, 0));
   if (per_sm < 1) return fail(c, B200RT_ERR_CUDA, "k_shade does not fit on an SM");
   w->shade_grid = per_sm * c->sm_count;
   int key = trav * 4 + (smem ? 2 : 0) + (stats ? 1 : 0);
@@ -450,7 +458,7 @@ int check_frame_args(b200rt_ctx *c, const float *cam, int width, int height, int
   if (o.rng_mode != B200RT_RNG_REFERENCE && o.rng_mode != B200RT_RNG_PHILOX)
     return fail(c, B200RT_ERR_INVALID, "bad rng_mode %d", o.rng_mode);
   if (o.traversal < 0 || o.traversal > 2) return fail(c, B200RT_ERR_INVALID, "bad traversal %d", o.traversal);
-  if (o.sampling != B200RT_SAMPLING_REFERENCE && o.sampling != B200RT_SAMPLING_IMPORTANCE)
+  if (o.sampling < 0 || o.sampling > (B200RT_SAMPLING_IMPORTANCE | B200RT_SAMPLING_LIGHTS))
     return fail(c, B200RT_ERR_INVALID, "bad sampling mode %d", o.sampling);
   if (o.output != B200RT_OUT_FINAL && o.output != B200RT_OUT_SUMS)
     return fail(c, B200RT_ERR_INVALID, "bad output mode %d", o.output);
@@ -485,8 +493,11 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   frame_setup(c, cam, env, width, height, spp, max_bounce, o, &F);
   // every live path traces exactly one ray per iteration and a sample needs at most max_bounce + 1 bounce rays
   // plus one sun ray (Raytracing.cl:46-137)
-  const long long n_iter_ll = (long long)(F.s1 - F.s0) * ((long long)max_bounce + 2);
-  if (n_iter_ll > (1 << 22)) return fail(c, B200RT_ERR_UNSUPPORTED, "spp x (maxBounce + 2) = %lld wavefront iterations exceed 2^22", n_iter_ll);
+  // with light sampling every surface that scatters adds one shadow ray towards an emitter: up to 2 (max_bounce + 1) + 1
+  const bool nee = (o.sampling & B200RT_SAMPLING_LIGHTS) != 0 && c->n_light > 0;
+  const long long per_sample = nee ? 2 * ((long long)max_bounce + 1) + 1 : (long long)max_bounce + 2;
+  const long long n_iter_ll = (long long)(F.s1 - F.s0) * per_sample;
+  if (n_iter_ll > (1 << 22)) return fail(c, B200RT_ERR_UNSUPPORTED, "%lld wavefront iterations exceed 2^22", n_iter_ll);
   const int n_iter = (int)n_iter_ll;
   if (ensure(c, c->d_prim_dirk, npix * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_prim_tri, npix * sizeof(int))) return B200RT_ERR_CUDA;
@@ -494,6 +505,11 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   if (ensure(c, c->d_pB, npix * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_pC, npix * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_pHit, npix * sizeof(int2))) return B200RT_ERR_CUDA;
+  if (nee) {
+    if (ensure(c, c->d_pS, npix * sizeof(float4))) return B200RT_ERR_CUDA;
+    if (ensure(c, c->d_pL, npix * sizeof(float4))) return B200RT_ERR_CUDA;
+    if (ensure(c, c->d_pR, npix * sizeof(float4))) return B200RT_ERR_CUDA;
+  }
   if (ensure(c, c->d_list0, npix * sizeof(int))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_list1, npix * sizeof(int))) return B200RT_ERR_CUDA;
   const size_t n_work = (size_t)((width + 7) / 8) * ((height + 3) / 4) * 32;   // tile-ordered work items of k_primary
@@ -538,7 +554,8 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
   int n_compactions = 0;
   for (int it = 0; it <= n_iter; ++it) {
     if (o.time_kernels) CU(cudaEventRecord(c->kev[c->kev_used++], c->stream));
-    k_shade<<<wl.shade_grid, kShadeBlock, 0, c->stream>>>(A, it);
+    if (nee) k_shade<true><<<wl.shade_grid, kShadeBlock, 0, c->stream>>>(A, it);
+    else k_shade<false><<<wl.shade_grid, kShadeBlock, 0, c->stream>>>(A, it);
     if (it < n_iter && (it + 1) % A.compact_every == 0) {  // close the gaps the finished pixels left, order kept (timed with k_shade)
       k_compact<<<wl.shade_grid, kCompactBlock, 0, c->stream>>>(A.slots, A.cnt + it, 0u, A.part_count, A.list[(it + 1) & 1], A.cnt + it + 1);
       ++n_compactions;
@@ -566,6 +583,8 @@ void borrow_scene(b200rt_ctx *p, b200rt_ctx *h) {
   auto lend = [](DevBuf &dst, const DevBuf &src) { dst.p = src.p; dst.cap = src.cap; dst.borrowed = true; };
   lend(h->d_nodes, p->d_nodes); lend(h->d_tris, p->d_tris); lend(h->d_normals, p->d_normals); lend(h->d_tboxes, p->d_tboxes);
   lend(h->d_frames, p->d_frames); lend(h->d_mats, p->d_mats); lend(h->d_bvh9, p->d_bvh9); lend(h->d_leafcnt, p->d_leafcnt);
+  lend(h->d_light, p->d_light);
+  h->n_light = p->n_light;
   h->n_nodes9 = p->n_nodes9; h->n_inner = p->n_inner; h->n_tris = p->n_tris; h->n_mats = p->n_mats;
   h->node_f4 = p->node_f4; h->depth = p->depth; h->ref_stack_need = p->ref_stack_need; h->canonical = p->canonical;
   h->root_ref = p->root_ref;
@@ -766,7 +785,8 @@ void b200rt_destroy(b200rt_ctx *c) {
   }
   DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_frames, &c->d_mats, &c->d_bvh9, &c->d_leafcnt, &c->d_prim_dirk,
                     &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b, &c->d_pA, &c->d_pB, &c->d_pC,
-                    &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt, &c->d_slots, &c->d_part_count};
+                    &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt, &c->d_slots, &c->d_part_count, &c->d_light, &c->d_pS,
+                    &c->d_pL, &c->d_pR};
   for (DevBuf *b : bufs)
     if (b->p && !b->borrowed) cudaFree(b->p);
   if (c->ibl_tex) cudaDestroyTextureObject(c->ibl_tex);
@@ -795,6 +815,19 @@ int b200rt_set_materials(b200rt_ctx *c, const float *mat, int64_t n_mat) {
   if (c->n_mats == nm && c->mat_hash != 0 && h == c->mat_hash && c->d_mats.p) return 0;
   if (ensure(c, c->d_mats, (size_t)n_mat * 4)) return B200RT_ERR_CUDA;
   CU(cudaMemcpyAsync(c->d_mats.p, mat, (size_t)n_mat * 4, cudaMemcpyHostToDevice, c->stream));
+  // The emitter list of the opt-in light sampling: what FileManager.py:235-240 builds as lightData — the triangles
+  // whose material is emissive, in triangle order — derived here from the materials just given, so that it can never
+  // be stale after a material edit (the reference's kernel receives lightData and never reads it, Raytracing.cl:163).
+  {
+    std::vector<int32_t> lights;
+    for (size_t t = 0; t < c->tri_mat.size(); ++t)
+      if ((int)mat[6 * (size_t)c->tri_mat[t]] == 0) lights.push_back((int32_t)t);
+    c->n_light = (int)lights.size();
+    if (!lights.empty()) {
+      if (ensure(c, c->d_light, lights.size() * sizeof(int32_t))) return B200RT_ERR_CUDA;
+      CU(cudaMemcpy(c->d_light.p, lights.data(), lights.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+  }
   CU(cudaStreamSynchronize(c->stream));
   c->n_mats = nm;
   c->mat_hash = h;

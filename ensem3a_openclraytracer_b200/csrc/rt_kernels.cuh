@@ -32,8 +32,8 @@ struct DeviceCounters {
 //   pA = origin.xyz, dir.x     pB = dir.y, dir.z, meta, rng     pC = throughput.rgb, -     pHit = triangle, distance
 // origin / dir describe the ray in flight (for a sun ray `dir` keeps the escaped direction for the environment
 // lookup and the ray itself points along FrameParams::sun_dir).
-// meta: bit 0 first iteration (no ray traced yet), bit 3 sun ray, bits 4-7 material type of the surface the ray
-// left, bits 8-15 bounce j, bits 16-31 sample index
+// meta: bit 0 first iteration (no ray traced yet), bit 1 light ray (opt-in light sampling), bit 3 sun ray, bits 4-7
+// material type of the surface the ray left, bits 8-15 bounce j, bits 16-31 sample index
 struct KernelArgs {
   FrameParams F;
   SceneView S;            // global-memory view (the SMEM variant rebuilds node / triangle pointers)
@@ -41,8 +41,14 @@ struct KernelArgs {
   float4 *prim_dirk;      // per pixel: primary direction xyz, hit distance
   int *prim_tri;          // per pixel: primary triangle
   float *out;             // width*height*3: running sums, then the image
-  float4 *pA, *pB, *pC;
+  float4 *pA, *pB, *pC;   // pC.w: density with which the surface the ray left drew its direction (light sampling only)
   int2 *pHit;
+  // opt-in light sampling (k_shade<true>): the emitter triangles, and three more float4 of path state
+  const int *light;       // triangles whose material is emissive, ascending (what FileManager.py:235-240 lists)
+  int n_light;
+  float4 *pS;             // while a light ray is in flight: incoming direction at the surface, its triangle
+  float4 *pL;             //   and the weighted contribution that counts if the ray reaches the emitter `w`
+  float4 *pR;             // direct light gathered by the current sample
   int *list[2];           // live paths, ping-pong, ALWAYS in the order of the frame's 8x4-pixel tiles; -1 = a path that
                           // left the wavefront since the last compaction (k_shade and k_trace skip such entries)
   int *slots;             // k_primary's / k_shade's output on the iterations that are followed by a compaction
@@ -61,8 +67,8 @@ struct KernelArgs {
   int validate;           // 1: hits come from the conservative traversal and must pass validate_hit
 };
 
-RT_DEV uint32_t meta_pack(int first, int sun, int type, int j, int s) {
-  return (uint32_t)first | ((uint32_t)sun << 3) | ((uint32_t)(type & 15) << 4) | ((uint32_t)(j & 255) << 8) | ((uint32_t)s << 16);
+RT_DEV uint32_t meta_pack(int first, int sun, int type, int j, int s, int light = 0) {
+  return (uint32_t)first | ((uint32_t)light << 1) | ((uint32_t)sun << 3) | ((uint32_t)(type & 15) << 4) | ((uint32_t)(j & 255) << 8) | ((uint32_t)s << 16);
 }
 
 // ---- shared-memory staging of a small scene with the bulk-copy engine (TMA 1-D) ------------------------
@@ -295,7 +301,10 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact(const int *__restrict
 // The per-path state machine is written as a sequence of phases with the warp re-converged between them, so that
 // e.g. the direction sampling runs once per warp for every lane that needs it, whichever way the lane got there
 // (bounce hit, or sample ended and the next one starts from the cached primary hit).
-// 8 CTAs per SM: the kernel is bound by the latency of its gathers; 5-7 (no spills) and 9-12 resident CTAs were all slower
+// 8 CTAs per SM: the kernel is bound by the latency of its gathers; 5-7 (no spills) and 9-12 resident CTAs were all slower.
+// NEE = opt-in light sampling (b200rt_opts.sampling bit 1): a separate instantiation, so that the reference's
+// estimator runs exactly the code it ran before.
+template <bool NEE>
 __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant__ KernelArgs A, int iter) {
   const FrameParams &F = A.F;
   const SceneView &S = A.S;
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     rng_state g;
     g.a = 0u;
     v3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(0.0f, 0.0f, 1.0f), acc = mk3(1.0f, 1.0f, 1.0f);
-    float hk = 0.0f;
+    float hk = 0.0f, pb_ray = 0.0f;
     int htri = -1;
     if (valid) {
       const float4 sb = A.pB[pix];
@@ -338,6 +347,7 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
         o = mk3(sa.x, sa.y, sa.z);
         d = mk3(sa.w, sb.x, sb.y);
         acc = mk3(sc.x, sc.y, sc.z);
+        if (NEE) pb_ray = sc.w;
         htri = hh.x;
         hk = __int_as_float(hh.y);
       }
@@ -345,11 +355,13 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     const bool first = (meta & 1u) != 0u;
     int sun_ray = (int)((meta >> 3) & 1u), seg_type = (int)((meta >> 4) & 15u);
     int j = (int)((meta >> 8) & 255u), s = (int)(meta >> 16);
+    const bool light_ray = NEE && ((meta >> 1) & 1u) != 0u;
     bool pixel_done = false, start = valid && first, shade = false, end_sample = false, sun_done = false;
+    bool want_light = false, light_done = false, from_light = false;
 
     // ---- phase 1: the winner of the conservative walk must pass the exact leaf-box test ---------------------------------
     if (valid && !first && A.validate && htri != -1) {
-      const v3 dray = sun_ray ? F.sun_dir : d;
+      const v3 dray = sun_ray ? F.sun_dir : d;   // a light ray's direction sits in d
       if (htri == kHitNeedsExactWalk ||
           !validate_winner(S, o, dray, htri, __float_as_int(__ldg(S.tris + 3 * (size_t)htri + 2).z))) {  // out-of-range or grazing ray: re-trace exactly
         const Hit h = closest_hit_nodrop<false>(S, o, dray);
@@ -362,7 +374,9 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
 
     // ---- phase 2: resolve the traced ray (Raytracing.cl:91-137) ------------------------------------------------------------
     if (valid && !first) {
-      if (!sun_ray) {
+      if (light_ray) {
+        light_done = true;
+      } else if (!sun_ray) {
         if (htri >= 0) {  // the bounce ray becomes the current segment (:91-93)
           const int mat = __float_as_int(__ldg(S.tris + 3 * (size_t)htri + 2).y);
           const Material mb = load_material(S.mats, mat);
@@ -372,10 +386,18 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
               end_sample = true;
             } else {
               ++j;
-              shade = true;
+              if (NEE && mb.type != 3) want_light = true; else shade = true;
             }
           } else {  // :105-109
             acc = acc * mb.roughness;
+            if (NEE && seg_type != 3) {
+              // the light sample at the surface this ray left could have made the same connection: balance heuristic
+              const float4 t0 = __ldg(S.tris + 3 * (size_t)htri), t1 = __ldg(S.tris + 3 * (size_t)htri + 1);
+              const float4 t2 = __ldg(S.tris + 3 * (size_t)htri + 2);
+              const float pl = light_pdf(mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), A.n_light, unit(d), (hk * hk) * dot(d, d));
+              const float den = pb_ray + pl;
+              acc = acc * (den > 0.0f ? pb_ray / den : 0.0f);
+            }
             end_sample = true;
           }
         } else {  // escaped: shadow ray towards the sun from the same origin (:115-124); d keeps the escaped direction
@@ -406,9 +428,26 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
       end_sample = true;
     }
     __syncwarp();
+    if (NEE && light_done) {  // the light ray is back: its contribution counts iff it reached the emitter it aimed at
+      const float4 pl = A.pL[pix], ps = A.pS[pix];
+      if (htri == __float_as_int(pl.w)) {
+        float4 r = A.pR[pix];
+        r.x += pl.x; r.y += pl.y; r.z += pl.z;
+        A.pR[pix] = r;
+      }
+      d = mk3(ps.x, ps.y, ps.z);     // back at the surface: o is the light ray's origin, the surface point
+      htri = __float_as_int(ps.w);
+      hk = 0.0f;
+      from_light = true;
+      shade = true;
+    }
     if (end_sample) {
       float *acc_px = A.out + 3 * (size_t)pix;
       v3 sum = mk3(acc_px[0], acc_px[1], acc_px[2]);
+      if (NEE) {
+        const float4 r = A.pR[pix];
+        acc = mk3(r.x, r.y, r.z) + acc;   // direct light gathered along the path + what the path ended on
+      }
       sum = sum + acc;  // :207
       ++s;
       ++samples;
@@ -429,7 +468,41 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
       htri = A.prim_tri[pix];
       acc = mk3(1.0f, 1.0f, 1.0f);
       j = 0;
-      shade = true;
+      if (NEE) {
+        A.pR[pix] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const int mat0 = __float_as_int(__ldg(S.tris + 3 * (size_t)htri + 2).y);
+        if ((int)__ldg(S.mats + 6 * mat0) != 3) want_light = true; else shade = true;
+      } else {
+        shade = true;
+      }
+    }
+    __syncwarp();
+
+    // ---- phase 3b (light sampling only): one emitter point seen from the surface, and the shadow ray towards it --------------
+    if (NEE && want_light) {
+      const float4 t2 = __ldg(S.tris + 3 * (size_t)htri + 2);
+      const float4 nn = __ldg(S.normals + htri);
+      const v3 n = mk3(nn.x, nn.y, nn.z);
+      const Material m = load_material(S.mats, __float_as_int(t2.y));
+      const v3 un = unit(n);
+      float ul, ua, ub;
+      if (F.rng_mode == 0) draw3_light<0>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &ul, &ua, &ub);
+      else draw3_light<1>(g, (uint32_t)pix, (uint32_t)s, (uint32_t)j, F.key0, F.key1, &ul, &ua, &ub);
+      int idx = (int)(ul * (float)A.n_light);
+      if (idx > A.n_light - 1) idx = A.n_light - 1;
+      const int lt = __ldg(A.light + idx);
+      const float4 l0 = __ldg(S.tris + 3 * (size_t)lt), l1 = __ldg(S.tris + 3 * (size_t)lt + 1), l2 = __ldg(S.tris + 3 * (size_t)lt + 2);
+      const Material ml = load_material(S.mats, __float_as_int(l2.y));
+      const float Le = ml.type == 0 ? ml.roughness : 0.0f;
+      const v3 x = o + unit(d) * hk;
+      v3 w;
+      const v3 direct = sample_light(m, F.sampling, n, un, x, d, acc, mk3(l0.x, l0.y, l0.z), mk3(l0.w, l1.x, l1.y),
+                                     mk3(l1.z, l1.w, l2.x), Le, A.n_light, ua, ub, &w);
+      A.pS[pix] = make_float4(d.x, d.y, d.z, __int_as_float(htri));
+      A.pL[pix] = make_float4(direct.x, direct.y, direct.z, __int_as_float(lt));
+      o = x;
+      d = w;
+      sun_ray = 0;
     }
     __syncwarp();
 
@@ -454,12 +527,13 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
           nd = sample_cosine(n, tf, u0, u1, &inv_pdf);
           brdf = m.color * (1.0f / 3.14f);
         } else {
-          if (F.sampling == 1) nd = sample_glossy_importance(m.roughness, tf.un, d, u0, u1, &inv_pdf);
+          if (F.sampling & 1) nd = sample_glossy_importance(m.roughness, tf.un, d, u0, u1, &inv_pdf);
           else nd = sample_uniform(n, tf, u0, u1, &inv_pdf);
           brdf = bsdf_ggx(m, neg3(d), nd, n);
         }
       }
-      o = o + unit(d) * hk;  // :79 — no offset along the normal
+      if (NEE) pb_ray = m.type == 3 ? 0.0f : bsdf_pdf(m, F.sampling, tf.un, d, unit(nd));
+      if (!NEE || !from_light) o = o + unit(d) * hk;  // :79 — no offset along the normal
       d = nd;
       const float att = inv_pdf * fabsf(dot(nd, tf.un));
       acc = (acc * brdf) * att;
@@ -472,8 +546,9 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     const bool alive = valid && !pixel_done;
     if (alive) {
       A.pA[pix] = make_float4(o.x, o.y, o.z, d.x);
-      A.pB[pix] = make_float4(d.y, d.z, __uint_as_float(meta_pack(0, sun_ray, seg_type, j, s)), __uint_as_float(g.a));
-      A.pC[pix] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+      A.pB[pix] = make_float4(d.y, d.z, __uint_as_float(meta_pack(0, sun_ray, seg_type, j, s, (NEE && want_light) ? 1 : 0)),
+                              __uint_as_float(g.a));
+      A.pC[pix] = make_float4(acc.x, acc.y, acc.z, NEE ? pb_ray : 0.0f);
     }
     if (in_part) out[t] = alive ? pix : -1;
     survivors += alive ? 1u : 0u;

@@ -192,4 +192,28 @@ RT_DEV void draw2(rng_state &g, uint32_t pixel, uint32_t sample, uint32_t bounce
   }
 }
 
+// Three uniform draws for the light sample of bounce `j` (opt-in light sampling): the generator's next three values
+// in reference mode, the second Philox block of (pixel, sample, bounce) otherwise (the first feeds draw2).
+template <int RNG>
+RT_DEV void draw3_light(rng_state &g, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t k0, uint32_t k1,
+                        float *u0, float *u1, float *u2) {
+  if (RNG == 0) {
+    float u[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t b = 36969u * (g.a & 65535u) + (g.a >> 16);
+      const uint32_t a = 18000u * (b & 65535u) + (b >> 16);
+      u[i] = bits_to_unit((b << 16) + a);
+      g.a = a;
+    }
+    *u0 = u[0]; *u1 = u[1]; *u2 = u[2];
+  } else {
+    uint32_t o[4];
+    philox4x32_10(pixel, sample, bounce, 1u, k0, k1, o);
+    *u0 = bits_to_unit(o[0]);
+    *u1 = bits_to_unit(o[1]);
+    *u2 = bits_to_unit(o[2]);
+  }
+}
+
 }  // namespace b200rt

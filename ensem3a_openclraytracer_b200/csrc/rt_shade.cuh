@@ -204,6 +204,26 @@ RT_DEV v3 bsdf_ggx(const Material &m, v3 v, v3 l, v3 n) {
 // BRDF_GGX * |cos| * inv_pdf is an estimator of the same integral.  u0 picks the lobe and is stretched back to [0, 1).
 // A view direction below the surface (the reference does not flip normals) uses the cosine lobe alone.
 // The test-side CPU restatement mirrors this statement order, so images stay bit-identical to it.
+// density (per solid angle) with which sample_glossy_importance draws direction l; N, Vw unit vectors
+RT_DEV float glossy_mix_pdf(float al, v3 N, v3 Vw, v3 l) {
+  const float kPi = 3.14159265f;
+  const float ndv = dot(N, Vw);
+  const float ndl = dot(N, l);
+  const float pdf_cos = fmaxf(ndl, 0.0f) / kPi;
+  float pdf_spec = 0.0f;
+  if (ndv > 0.0f && ndl > 0.0f) {
+    const v3 h = unit(l + Vw);
+    const float ndh = dot(N, h);
+    const float a2 = al * al;
+    const float dden = ndh * ndh * (a2 - 1.0f) + 1.0f;
+    const float D = a2 / (kPi * dden * dden);
+    const float G1 = (2.0f * ndv) / (ndv + sqrtf(a2 + (1.0f - a2) * ndv * ndv));
+    pdf_spec = (G1 * D) / (4.0f * ndv);
+  }
+  const float ps = ndv > 0.0f ? 0.5f : 0.0f;
+  return ps * pdf_spec + (1.0f - ps) * pdf_cos;
+}
+
 RT_DEV v3 sample_glossy_importance(float roughness, v3 un, v3 d_in, float u0, float u1, float *inv_pdf) {
   const float kPi = 3.14159265f, kTwoPi = 6.2831853f;
   const v3 N = un;
@@ -243,22 +263,66 @@ RT_DEV v3 sample_glossy_importance(float roughness, v3 un, v3 d_in, float u0, fl
   } else {
     l = ((T * (r * cp)) + (B * (r * sp))) + (N * sqrtf(fmaxf(0.0f, 1.0f - u0r)));
   }
-  const float ndl = dot(N, l);
-  const float pdf_cos = fmaxf(ndl, 0.0f) / kPi;
-  float pdf_spec = 0.0f;
-  if (ndv > 0.0f && ndl > 0.0f) {
-    const v3 h = unit(l + Vw);
-    const float ndh = dot(N, h);
-    const float a2 = al * al;
-    const float dden = ndh * ndh * (a2 - 1.0f) + 1.0f;
-    const float D = a2 / (kPi * dden * dden);
-    const float G1 = (2.0f * ndv) / (ndv + sqrtf(a2 + (1.0f - a2) * ndv * ndv));
-    pdf_spec = (G1 * D) / (4.0f * ndv);
-  }
-  const float ps = ndv > 0.0f ? 0.5f : 0.0f;
-  const float pdf = ps * pdf_spec + (1.0f - ps) * pdf_cos;
-  *inv_pdf = pdf > 0.0f ? 1.0f / pdf : 0.0f;
+  const float pdf = glossy_mix_pdf(al, N, Vw, l);
+  // the reference's uniform sampler weighs with 2 * 3.14 where the true density is 1 / (2 pi): its expectation is
+  // 3.14 / pi times the integral.  Kept, so that both samplers converge to the same image.
+  *inv_pdf = pdf > 0.0f ? (3.14f / kPi) / pdf : 0.0f;
   return l;
+}
+
+// ---- opt-in: direct sampling of the emitters (b200rt_opts.sampling bit 1) ---------------------------------
+// Not in the reference, whose kernel receives lightData and never reads it (Raytracing.cl:163); the author's intent is
+// the dead sampleLight, MathLib.cl:404-454.  At every surface that scatters (types 1, 2) one emitter triangle is chosen
+// uniformly and one point uniformly on it; a shadow ray decides visibility.  The emitter is then reachable two ways — by
+// this light sample and by the surface's own direction sample happening to hit it — and both are kept with
+// balance-heuristic weights p / (p_light + p_bsdf) (densities per solid angle), which keeps the estimate bounded next to
+// a large emitter.  Same expectation as the reference's estimator: emission is the material's power (roughness slot,
+// Raytracing.cl:105-109) from both faces, the diffuse factor is color / pi and the glossy one 3.14 / pi x BRDF_GGX, which
+// is what the reference's samplers converge to.  The test-side CPU restatement mirrors the statement order.
+
+// density per solid angle with which the light sampler reaches the point at squared distance dist2 along unit direction
+// wi on emitter triangle (A, e1, e2); 0 when the triangle is seen edge-on
+RT_DEV float light_pdf(v3 e1, v3 e2, int n_light, v3 wi, float dist2) {
+  const v3 NL = cross(e1, e2);
+  const float area2 = sqrtf(dot(NL, NL));
+  const float cosL = fabsf(dot(NL, wi)) / area2;
+  if (!(cosL > 0.0f) || !(area2 > 0.0f)) return 0.0f;
+  return dist2 / ((cosL * ((float)n_light * 0.5f)) * area2);
+}
+
+// density per solid angle with which the surface's own sampler draws unit direction l (m.type 1 or 2)
+RT_DEV float bsdf_pdf(const Material &m, int sampling, v3 un, v3 d_in, v3 l) {
+  const float kPi = 3.14159265f;
+  const float ndl = dot(un, l);
+  if (m.type == 1) return fmaxf(ndl, 0.0f) / kPi;
+  if (sampling & 1) return glossy_mix_pdf(m.roughness, un, unit(neg3(d_in)), l);
+  return ndl > 0.0f ? 1.0f / (2.0f * kPi) : 0.0f;
+}
+
+// the weighted contribution of one light sample seen from surface point x (throughput `acc` before this surface's own
+// factor); *w_out is the shadow ray's direction (y - x, so the emitter lies at parameter 1)
+RT_DEV v3 sample_light(const Material &m, int sampling, v3 n, v3 un, v3 x, v3 d_in, v3 acc, v3 A, v3 e1, v3 e2, float Le,
+                       int n_light, float ua, float ub, v3 *w_out) {
+  const float kPi = 3.14159265f;
+  if (ua + ub > 1.0f) { ua = 1.0f - ua; ub = 1.0f - ub; }
+  const v3 y = (A + (e1 * ua)) + (e2 * ub);
+  const v3 w = y - x;
+  const float dist2 = dot(w, w);
+  const float dist = sqrtf(dist2);
+  const v3 wi = w / dist;
+  const float cosS = dot(wi, un);
+  v3 fr;
+  if (m.type == 1) {
+    fr = m.color * (1.0f / kPi);
+  } else {
+    fr = bsdf_ggx(m, neg3(d_in), wi, n) * (3.14f / kPi);
+  }
+  *w_out = w;
+  if (!(cosS > 0.0f) || !(dist2 > 0.0f)) return mk3(0.0f, 0.0f, 0.0f);
+  const float pl = light_pdf(e1, e2, n_light, wi, dist2);
+  if (!(pl > 0.0f)) return mk3(0.0f, 0.0f, 0.0f);
+  const float pb = bsdf_pdf(m, sampling, un, d_in, wi);
+  return (acc * fr) * ((cosS * Le) / (pl + pb));
 }
 
 }  // namespace b200rt

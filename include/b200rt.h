@@ -40,12 +40,18 @@ typedef enum {
 #define B200RT_TRAVERSAL_REFERENCE 1 /* the reference's visiting order incl. its capped stack (stack.cl:21-26) */
 #define B200RT_TRAVERSAL_VERIFY 2    /* runs both per ray, counts disagreements in stats.mismatches, keeps REFERENCE */
 
-/* direction sampling on glossy (type 2) surfaces — SURVEY.md 8f-4, opt-in, changes the image (same expectation) */
-#define B200RT_SAMPLING_REFERENCE 0  /* uniform hemisphere, the GGX BRDF as a weight (MathLib.cl:342-366, Raytracing.cl:63-66) */
+/* better estimators of the same integral — SURVEY.md 8f-4, opt-in bit mask, changes the image (same expectation) */
+#define B200RT_SAMPLING_REFERENCE 0  /* the reference's: uniform hemisphere with the GGX BRDF as a weight on glossy
+                                        surfaces (MathLib.cl:342-366, Raytracing.cl:63-66), emitters found by chance */
 #define B200RT_SAMPLING_IMPORTANCE 1 /* one-sample mixture of GGX visible-normal sampling (the lobe the author's dead
                                         rand_sample_GGX aims at, MathLib.cl:369-387) and cosine sampling of the BRDF's
                                         diffuse term; the same BRDF_GGX * cos / pdf estimator, far less variance at low
                                         roughness */
+#define B200RT_SAMPLING_LIGHTS 2     /* direct sampling of the emissive triangles (the list FileManager.py:235-240 calls
+                                        lightData; the reference kernel receives it and never reads it, Raytracing.cl:163;
+                                        intent: the dead sampleLight, MathLib.cl:404-454) at every surface that scatters,
+                                        combined with the surface's own sample by the balance heuristic; one more ray per
+                                        such surface, three more float4 of path state */
 
 /* output modes */
 #define B200RT_OUT_FINAL 0 /* mean over spp, clamped to [0,1]  (Raytracing.cl:211-219) */
@@ -73,7 +79,7 @@ typedef struct {
                              flight, which fills the GPU on small frames and overlaps shading with tracing on large ones.
                              -1: chosen from the frame size (2 from 1 Mpixel, 4 from 0.2 Mpixel, else 8).  The image equals
                              the one-stream image up to the order of N float additions per pixel. */
-  int32_t sampling;       /* B200RT_SAMPLING_*: 0 the reference's estimator (default); 1 importance sampling of glossy surfaces */
+  int32_t sampling;       /* bit mask of B200RT_SAMPLING_*; 0 = the reference's estimator (default) */
 } b200rt_opts;
 
 typedef struct {

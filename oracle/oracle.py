@@ -19,7 +19,8 @@ _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 class OrcOpts(ctypes.Structure):
     _fields_ = [("rng_mode", ctypes.c_int), ("seed_lo", ctypes.c_uint32), ("seed_hi", ctypes.c_uint32),
                 ("stack_cap", ctypes.c_int), ("s0", ctypes.c_int), ("s1", ctypes.c_int),
-                ("raw_sums", ctypes.c_int), ("nthreads", ctypes.c_int), ("sampling", ctypes.c_int)]
+                ("raw_sums", ctypes.c_int), ("nthreads", ctypes.c_int), ("sampling", ctypes.c_int),
+                ("n_light", ctypes.c_int), ("light", ctypes.c_void_p)]
 
 
 def build(verbose=False):
@@ -70,8 +71,10 @@ def render(scene, cam, env, img_dim, spp, max_bounce, ibl_rgba, i0=0, i1=None, r
     out = np.zeros(img_dim * 3, dtype=np.float32)
     ibl = np.ascontiguousarray(ibl_rgba, dtype=np.uint8)
     h, w = ibl.shape[0], ibl.shape[1]
+    light = np.ascontiguousarray(scene.get("lightData", np.zeros(0, np.int32)), dtype=np.int32)
     opts = OrcOpts(rng_mode, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, stack_cap, s0, s1,
-                   1 if raw_sums else 0, nthreads, sampling)
+                   1 if raw_sums else 0, nthreads, sampling, int(light.size),
+                   light.ctypes.data_as(ctypes.c_void_p) if light.size else None)
     cnt = (ctypes.c_ulonglong * 4)()
     face = scene["faceData"]
     lib.orc_render(out, scene["V_p"], scene["V_n"], scene["V_uv"], face, scene["materialData"], scene["BVH"],

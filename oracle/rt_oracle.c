@@ -76,7 +76,10 @@ typedef struct {
   int s0, s1;          /* sample range [s0,s1); s1 <= 0 means [0, spp) */
   int raw_sums;        /* 1: write the un-normalised, un-clamped sum over [s0,s1) */
   int nthreads;        /* 0 = OpenMP default */
-  int sampling;        /* 0 = the reference's estimator; 1 = importance sampling of glossy surfaces (opt-in) */
+  int sampling;        /* bit 0: importance sampling of glossy surfaces; bit 1: direct sampling of the emitters listed in
+                          `light` (opt-in); 0 = the reference's estimator */
+  int n_light;         /* lightData as FileManager builds it (FileManager.py:235-240): triangles whose material is emissive */
+  const int *light;
 } orc_opts;
 
 typedef struct {
@@ -88,6 +91,8 @@ typedef struct {
   const float *cam, *env;
   int stack_cap;
   int sampling;
+  int n_light;
+  const int *light;
 } scene_t;
 
 /* =========================================================================================
@@ -356,6 +361,27 @@ static v3 sample_uniform(v3 n, rng_t *g, float *inv_pdf) {
  * distribution of BRDF_GGX, MathLib.cl:470-472; the lobe the author's dead rand_sample_GGX aims at, :369-387) and a
  * cosine lobe for the BRDF's diffuse term; returns the direction and 1 / pdf of the mixture.  Restated statement by
  * statement from csrc/rt_shade.cuh::sample_glossy_importance so that the two agree bit for bit. */
+/* density (per solid angle) with which sample_glossy_importance draws direction l: half GGX visible normals reflected,
+ * half cosine lobe; the cosine lobe alone when the viewer is below the surface.  N, Vw unit vectors. */
+static float glossy_mix_pdf(float al, v3 N, v3 Vw, v3 l) {
+  const float kPi = 3.14159265f;
+  float ndv = dot3(N, Vw);
+  float ndl = dot3(N, l);
+  float pdf_cos = fmaxf(ndl, 0.0f) / kPi;
+  float pdf_spec = 0.0f;
+  if (ndv > 0.0f && ndl > 0.0f) {
+    v3 h = unit3(add3(l, Vw));
+    float ndh = dot3(N, h);
+    float a2 = al * al;
+    float dden = ndh * ndh * (a2 - 1.0f) + 1.0f;
+    float D = a2 / (kPi * dden * dden);
+    float G1 = (2.0f * ndv) / (ndv + sqrtf(a2 + (1.0f - a2) * ndv * ndv));
+    pdf_spec = (G1 * D) / (4.0f * ndv);
+  }
+  float ps = ndv > 0.0f ? 0.5f : 0.0f;
+  return ps * pdf_spec + (1.0f - ps) * pdf_cos;
+}
+
 static v3 sample_glossy_importance(float roughness, v3 n, v3 d_in, rng_t *g, float *inv_pdf) {
   const float kPi = 3.14159265f, kTwoPi = 6.2831853f;
   float u0 = rng_next(g);
@@ -396,21 +422,10 @@ static v3 sample_glossy_importance(float roughness, v3 n, v3 d_in, rng_t *g, flo
   } else {
     l = add3(add3(scale3(T, r * cp), scale3(B, r * sp)), scale3(N, sqrtf(fmaxf(0.0f, 1.0f - u0r))));
   }
-  float ndl = dot3(N, l);
-  float pdf_cos = fmaxf(ndl, 0.0f) / kPi;
-  float pdf_spec = 0.0f;
-  if (ndv > 0.0f && ndl > 0.0f) {
-    v3 h = unit3(add3(l, Vw));
-    float ndh = dot3(N, h);
-    float a2 = al * al;
-    float dden = ndh * ndh * (a2 - 1.0f) + 1.0f;
-    float D = a2 / (kPi * dden * dden);
-    float G1 = (2.0f * ndv) / (ndv + sqrtf(a2 + (1.0f - a2) * ndv * ndv));
-    pdf_spec = (G1 * D) / (4.0f * ndv);
-  }
-  float ps = ndv > 0.0f ? 0.5f : 0.0f;
-  float pdf = ps * pdf_spec + (1.0f - ps) * pdf_cos;
-  *inv_pdf = pdf > 0.0f ? 1.0f / pdf : 0.0f;
+  float pdf = glossy_mix_pdf(al, N, Vw, l);
+  /* the reference's uniform sampler weighs with 2 * 3.14 where the true density is 1 / (2 pi): its expectation is
+   * 3.14 / pi times the integral.  Kept, so that both samplers converge to the same image. */
+  *inv_pdf = pdf > 0.0f ? (3.14f / kPi) / pdf : 0.0f;
   return l;
 }
 
@@ -437,6 +452,92 @@ static v3 bsdf_ggx(const mat_t *m, v3 v, v3 l, v3 n) {
   return V(diffuse.x + spec, diffuse.y + spec, diffuse.z + spec);
 }
 
+/* ---- opt-in light sampling (orc_opts.sampling bit 1) -----------------------------------------------------------------
+ * NOT in the reference, whose kernel receives lightData and never reads it (Raytracing.cl:163); the author's intent is
+ * the dead sampleLight, MathLib.cl:404-454.  At every surface that scatters (types 1, 2) one emitter triangle is chosen
+ * uniformly from lightData and one point uniformly on it; a shadow ray decides visibility.  The emitter is then reachable
+ * two ways — by this light sample and by the surface's own direction sample happening to hit it — and both are kept with
+ * balance-heuristic weights p / (p_light + p_bsdf) (densities per solid angle), which keeps the estimate bounded next to a
+ * large emitter where light sampling alone has unbounded variance.  Same expectation as the reference's estimator:
+ * emission is the material's power (roughness slot, Raytracing.cl:105-109) from both faces, the diffuse factor is
+ * color / pi and the glossy one 3.14 / pi x BRDF_GGX, which is what the reference's samplers converge to.
+ * Mirrors csrc/rt_shade.cuh statement by statement. */
+
+/* density per solid angle with which the light sampler reaches the point at squared distance dist2 along unit direction
+ * wi on emitter triangle t; 0 when the triangle is seen edge-on */
+static float light_pdf(const scene_t *sc, int t, v3 wi, float dist2) {
+  const int *f = sc->face + 10 * t;
+  const float *pa = sc->vp + 3 * f[7], *pb = sc->vp + 3 * f[8], *pc = sc->vp + 3 * f[9];
+  v3 A = V(pa[0], pa[1], pa[2]);
+  v3 e1 = sub3(V(pb[0], pb[1], pb[2]), A);
+  v3 e2 = sub3(V(pc[0], pc[1], pc[2]), A);
+  v3 NL = cross3(e1, e2);
+  float area2 = sqrtf(dot3(NL, NL));
+  float cosL = fabsf(dot3(NL, wi)) / area2;
+  if (!(cosL > 0.0f) || !(area2 > 0.0f)) return 0.0f;
+  return dist2 / ((cosL * ((float)sc->n_light * 0.5f)) * area2);
+}
+
+/* density per solid angle with which the surface's own sampler draws unit direction l (M.type 1 or 2) */
+static float bsdf_pdf(const scene_t *sc, const mat_t *M, v3 n, v3 d_in, v3 l) {
+  const float kPi = 3.14159265f;
+  v3 N = unit3(n);
+  float ndl = dot3(N, l);
+  if (M->type == 1) return fmaxf(ndl, 0.0f) / kPi;
+  if (sc->sampling & 1) return glossy_mix_pdf(M->roughness, N, unit3(V(-d_in.x, -d_in.y, -d_in.z)), l);
+  return ndl > 0.0f ? 1.0f / (2.0f * kPi) : 0.0f;
+}
+
+static v3 sample_light(const scene_t *sc, const mat_t *M, v3 n, v3 x, v3 d_in, v3 acc, const float u[3], ray_t *shadow,
+                       int *target) {
+  const float kPi = 3.14159265f;
+  int idx = (int)(u[0] * (float)sc->n_light);
+  if (idx > sc->n_light - 1) idx = sc->n_light - 1;
+  int t = sc->light[idx];
+  const int *f = sc->face + 10 * t;
+  const float *pa = sc->vp + 3 * f[7], *pb = sc->vp + 3 * f[8], *pc = sc->vp + 3 * f[9];
+  v3 A = V(pa[0], pa[1], pa[2]);
+  v3 e1 = sub3(V(pb[0], pb[1], pb[2]), A);
+  v3 e2 = sub3(V(pc[0], pc[1], pc[2]), A);
+  mat_t ML = material_at(sc, f[0]);
+  float Le = ML.type == 0 ? ML.roughness : 0.0f;
+  float ua = u[1], ub = u[2];
+  if (ua + ub > 1.0f) { ua = 1.0f - ua; ub = 1.0f - ub; }
+  v3 y = add3(add3(A, scale3(e1, ua)), scale3(e2, ub));
+  v3 w = sub3(y, x);
+  float dist2 = dot3(w, w);
+  float dist = sqrtf(dist2);
+  v3 wi = div3s(w, dist);
+  float cosS = dot3(wi, unit3(n));
+  v3 fr;
+  if (M->type == 1) {
+    fr = scale3(M->color, 1.0f / kPi);
+  } else {
+    fr = scale3(bsdf_ggx(M, V(-d_in.x, -d_in.y, -d_in.z), wi, n), 3.14f / kPi);
+  }
+  shadow->o = x;
+  shadow->d = w;
+  *target = t;
+  if (!(cosS > 0.0f) || !(dist2 > 0.0f)) return V(0.0f, 0.0f, 0.0f);
+  float pl = light_pdf(sc, t, wi, dist2);
+  if (!(pl > 0.0f)) return V(0.0f, 0.0f, 0.0f);
+  float pb_ = bsdf_pdf(sc, M, n, d_in, wi);
+  return scale3(mul3(acc, fr), (cosS * Le) / (pl + pb_));
+}
+
+/* three uniforms for the light sample of bounce j: the generator's next three values in reference mode, the second
+ * Philox block of (pixel, sample, bounce) otherwise (the first block feeds the direction sampling) */
+static void rng_light3(rng_t *g, uint32_t pixel, uint32_t sample, uint32_t bounce, float u[3]) {
+  if (g->mode == 0) {
+    u[0] = rng_next(g); u[1] = rng_next(g); u[2] = rng_next(g);
+    return;
+  }
+  uint32_t ctr[4] = {pixel, sample, bounce, 1u}, out[4];
+  philox4x32_10(ctr, g->key0, g->key1, out);
+  tl_cnt.rand_calls += 3;
+  u[0] = bits_to_unit(out[0]); u[1] = bits_to_unit(out[1]); u[2] = bits_to_unit(out[2]);
+}
+
 /* =========================================================================================
  * One sample — Raytracing.cl:39-153
  * ======================================================================================= */
@@ -451,6 +552,8 @@ static v3 sun_direction(const scene_t *sc) { /* Raytracing.cl:115-118 */
 static v3 path_sample(const scene_t *sc, int max_bounce, hit_t H, ray_t R, mat_t M, rng_t *g,
                       uint32_t pixel, uint32_t sample) {
   v3 acc = V(1.0f, 1.0f, 1.0f);
+  v3 rad = V(0.0f, 0.0f, 0.0f);      /* direct light gathered along the path (light sampling only) */
+  const int nee = (sc->sampling & 2) && sc->n_light > 0;
   for (int j = 0; j <= max_bounce; ++j) {
     rng_set_bounce(g, pixel, sample, (uint32_t)j);
     if (!H.hit) { /* :146-150 */
@@ -461,17 +564,28 @@ static v3 path_sample(const scene_t *sc, int max_bounce, hit_t H, ray_t R, mat_t
       acc = scale3(acc, M.roughness);
       break;
     }
+    if (nee && M.type != 3) {   /* emitters are sampled at every surface that scatters (not at pass-through glass) */
+      float u[3];
+      rng_light3(g, pixel, sample, (uint32_t)j, u);
+      ray_t sh;
+      int target;
+      v3 x = add3(R.o, scale3(unit3(R.d), H.k));
+      v3 direct = sample_light(sc, &M, H.n, x, R.d, acc, u, &sh, &target);
+      hit_t Hl = closest_hit(sc, &sh);
+      if (Hl.hit && Hl.tri == target) rad = add3(rad, direct);
+    }
     ray_t nb;
     v3 brdf = V(0, 0, 0);
     float inv_pdf = 0.0f;
     nb.d = V(0, 0, 0);
+    const v3 d_in = R.d;
     switch (M.type) { /* :58-78 (case 0 is unreachable here) */
       case 1:
         nb.d = sample_cosine(H.n, g, &inv_pdf);
         brdf = scale3(M.color, 1.0f / 3.14f);
         break;
       case 2:
-        if (sc->sampling == 1) nb.d = sample_glossy_importance(M.roughness, H.n, R.d, g, &inv_pdf);
+        if (sc->sampling & 1) nb.d = sample_glossy_importance(M.roughness, H.n, R.d, g, &inv_pdf);
         else nb.d = sample_uniform(H.n, g, &inv_pdf);
         brdf = bsdf_ggx(&M, V(-R.d.x, -R.d.y, -R.d.z), nb.d, H.n);
         break;
@@ -488,12 +602,21 @@ static v3 path_sample(const scene_t *sc, int max_bounce, hit_t H, ray_t R, mat_t
     acc = scale3(mul3(acc, brdf), att);
     if (Hb.hit) {
       int from_type = M.type;
-      (void)from_type;
+      mat_t Mfrom = M;
+      v3 nfrom = H.n;
       R = nb; H = Hb; M = Mb;
       if (Mb.type != 0) {
         if (j == max_bounce) { acc = V(0, 0, 0); break; }
       } else {
         acc = scale3(acc, Mb.roughness);
+        if (nee && from_type != 3) {
+          /* the light sample at the surface this ray left could have produced the same connection: balance heuristic */
+          v3 wi = unit3(nb.d);
+          float pb_ = bsdf_pdf(sc, &Mfrom, nfrom, d_in, wi);
+          float pl = light_pdf(sc, Hb.tri, wi, (Hb.k * Hb.k) * dot3(nb.d, nb.d));
+          float den = pb_ + pl;
+          acc = scale3(acc, den > 0.0f ? pb_ / den : 0.0f);
+        }
         break;
       }
     } else { /* escaped: sun shadow ray + environment, :111-138 */
@@ -510,7 +633,7 @@ static v3 path_sample(const scene_t *sc, int max_bounce, hit_t H, ray_t R, mat_t
       break;
     }
   }
-  return acc;
+  return nee ? add3(rad, acc) : acc;
 }
 
 /* =========================================================================================
@@ -520,6 +643,8 @@ static void fill_scene(scene_t *sc, const float *vp, const float *vn, const floa
                        const float *mat, const float *bvh, const float *cam, const float *env,
                        int tri_count, const unsigned char *ibl, int ibl_w, int ibl_h, int stack_cap) {
   sc->sampling = 0;
+  sc->n_light = 0;
+  sc->light = NULL;
   sc->vp = vp; sc->vn = vn; sc->vuv = vuv; sc->face = face; sc->mat = mat; sc->bvh = bvh;
   sc->cam = cam; sc->env = env; sc->tri_count = tri_count;
   sc->ibl = ibl; sc->ibl_w = ibl_w; sc->ibl_h = ibl_h;
@@ -535,6 +660,8 @@ void orc_render(float *out, const float *vp, const float *vn, const float *vuv, 
   scene_t sc;
   fill_scene(&sc, vp, vn, vuv, face, mat, bvh, cam, env, tri_count, ibl, ibl_w, ibl_h, opts->stack_cap);
   sc.sampling = opts->sampling;
+  sc.n_light = opts->light ? opts->n_light : 0;
+  sc.light = opts->light;
   int s0 = opts->s0, s1 = opts->s1;
   if (s1 <= 0) { s0 = 0; s1 = spp; }
   unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;

@@ -606,3 +606,64 @@ def test_importance_sampling_has_the_same_mean_and_less_variance(gpu_ctx):
     noise_ref = np.sqrt(np.mean((img[0, 1] - img[0, 2]) ** 2))
     noise_imp = np.sqrt(np.mean((img[1, 1] - img[1, 2]) ** 2))
     assert noise_imp < 0.5 * noise_ref
+
+
+def lit_cornell():
+    """the Cornell box with its lamp switched on (the shipped .ini has power 0) and no sun: every photon comes from the lamp"""
+    sc = dict(fixtures.load_scene("cornell"))
+    m = sc["materialData"].copy().reshape(-1, 6)
+    m[3, 4] = 5.0
+    sc["materialData"] = m.reshape(-1)
+    sc["params"] = dict(sc["params"], sun_Power="0")
+    return sc
+
+
+@pytest.mark.parametrize("which", ["lit_cornell", "monkey_cfg2"])
+def test_opt_in_light_sampling_matches_its_oracle_mode(gpu_ctx, which):
+    """SURVEY 8f-4, opt-in: b200rt_opts.sampling bit 1 samples the emitter triangles at every surface that scatters and
+    weighs that against the surface's own direction sample (balance heuristic).  Not the reference's image (same
+    expectation) — held, bit for bit, to the oracle's restatement, alone and together with the glossy importance
+    sampling, in both generators; ray counts included (one more ray per scattering surface)."""
+    sc = lit_cornell() if which == "lit_cornell" else fixtures.load_scene(which)
+    ibl = fixtures.load_ibl()
+    fixtures.upload(gpu_ctx, sc, ibl)
+    # the emitter list the library derives from the materials is the one FileManager builds
+    emissive = [t for t in range(sc["faceData"].size // 10) if int(sc["materialData"][6 * sc["faceData"][10 * t]]) == 0]
+    assert emissive == list(sc["lightData"])
+    res, spp = 64, 5
+    cam, env = fixtures.cam_env(sc["params"], res)
+    for rng, orng in ((rt.RNG_REFERENCE, oracle.RNG_REFERENCE), (rt.RNG_PHILOX, oracle.RNG_PHILOX)):
+        for mode in (rt.SAMPLING_LIGHTS, rt.SAMPLING_LIGHTS | rt.SAMPLING_IMPORTANCE):
+            for bounce in (4, 0):
+                want, cnt = oracle.render(sc, cam, env, res * res, spp, bounce, ibl, rng_mode=orng, seed=4, sampling=mode)
+                got = gpu_ctx.render(cam, env, res, res, spp, bounce, opts=rt.make_opts(rng_mode=rng, seed=4, sampling=mode))
+                assert gpu_ctx.stats()["rays"] == cnt["rays"]
+                assert_radiance(got, want)
+                assert np.array_equal(bits(got), bits(want))
+    # sample streams and sample ranges compose with it
+    a = gpu_ctx.render(cam, env, res, res, 6, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=4, sampling=rt.SAMPLING_LIGHTS))
+    b = gpu_ctx.render(cam, env, res, res, 6, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=4, sampling=rt.SAMPLING_LIGHTS,
+                                                                   sample_streams=3))
+    rel = np.abs(a - b) / np.maximum(np.abs(a), REL_FLOOR)
+    assert rel.max() <= REL_TOL
+
+
+def test_light_sampling_has_the_same_mean_and_less_variance(gpu_ctx):
+    """Lit Cornell box, lamp only: the mean radiance agrees with the reference estimator's to 1 %, and at equal spp the
+    pixel noise drops by more than 2x (the lamp is a small part of every surface's hemisphere)."""
+    sc = lit_cornell()
+    ibl = fixtures.load_ibl()
+    fixtures.upload(gpu_ctx, sc, ibl)
+    res, spp = 160, 256
+    cam, env = fixtures.cam_env(sc["params"], res)
+    img = {}
+    for mode in (rt.SAMPLING_REFERENCE, rt.SAMPLING_LIGHTS):
+        for seed in (1, 2):
+            img[mode, seed] = gpu_ctx.render(cam, env, res, res, spp, 4, opts=rt.make_opts(rng_mode=rt.RNG_PHILOX, seed=seed,
+                                                                                           sampling=mode, output=rt.OUT_SUMS)) / spp
+    m_ref = 0.5 * (img[0, 1].mean() + img[0, 2].mean())
+    m_nee = 0.5 * (img[2, 1].mean() + img[2, 2].mean())
+    assert abs(m_ref - m_nee) <= 0.01 * m_ref
+    noise_ref = np.sqrt(np.mean((img[0, 1] - img[0, 2]) ** 2))
+    noise_nee = np.sqrt(np.mean((img[2, 1] - img[2, 2]) ** 2))
+    assert noise_nee < 0.5 * noise_ref

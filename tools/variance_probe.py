@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Variance at equal spp of the opt-in glossy importance sampling (b200rt_opts.sampling = 1) against the reference's
-uniform-hemisphere estimator, on fixture scenes: RMSE of an spp-sample image against a converged image of the SAME
-integrand (the mean of both estimators' long runs), per sampler.  One JSON line per scene.
+"""Variance at equal spp of the opt-in estimators (b200rt_opts.sampling: 1 glossy importance sampling, 2 light sampling,
+3 both) against the reference's, on fixture scenes: RMSE of an spp-sample image against a converged image of the SAME
+integrand (the mean of all estimators' long runs), per estimator, with the rays and device time each one spends.  One
+JSON line per scene.
 usage: variance_probe.py [spp=64] [converged_spp=8192] [scene:w:h:ibl ...]"""
 import json
 import os
@@ -33,22 +34,25 @@ def main():
             out = ctx.render(cam, env, w, h, n, 4, opts=o)
             return out.astype(np.float64) / n, ctx.stats()
 
-        conv_ref, _ = sums(rt.SAMPLING_REFERENCE, 1000, big)
-        conv_imp, _ = sums(rt.SAMPLING_IMPORTANCE, 2000, big)
-        truth = 0.5 * (conv_ref + conv_imp)
+        modes = ((0, "reference"), (1, "importance"), (2, "lights"), (3, "importance_lights"))
+        conv = {m: sums(m, 1000 + m, big)[0] for m, _ in modes}
+        truth = sum(conv.values()) / len(conv)
         line = dict(scene=name, width=w, height=h, spp=spp, converged_spp=big,
-                    converged_mean_reference=float(conv_ref.mean()), converged_mean_importance=float(conv_imp.mean()),
-                    rmse_between_converged_images=float(np.sqrt(np.mean((conv_ref - conv_imp) ** 2))))
-        for mode, key in ((rt.SAMPLING_REFERENCE, "reference"), (rt.SAMPLING_IMPORTANCE, "importance")):
-            errs, ms = [], []
+                    converged_means={k: float(conv[m].mean()) for m, k in modes})
+        for mode, key in modes:
+            errs, ms, rays = [], [], []
             for seed in range(4):
                 img, st = sums(mode, seed, spp)
                 errs.append(np.sqrt(np.mean((img - truth) ** 2)))
                 ms.append(st["total_ms"])
+                rays.append(st["rays"])
             line[f"rmse_{key}"] = float(np.mean(errs))
             line[f"device_ms_{key}"] = float(np.mean(ms))
-        line["rmse_ratio"] = line["rmse_reference"] / line["rmse_importance"]
-        line["equal_error_sample_ratio"] = line["rmse_ratio"] ** 2
+            line[f"rays_{key}"] = float(np.mean(rays))
+        for _, key in modes[1:]:
+            r = line["rmse_reference"] / line[f"rmse_{key}"]
+            line[f"samples_saved_at_equal_error_{key}"] = r * r
+            line[f"time_saved_at_equal_error_{key}"] = r * r * line["device_ms_reference"] / line[f"device_ms_{key}"]
         print(json.dumps(line), flush=True)
 
 
