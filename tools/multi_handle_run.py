@@ -33,7 +33,7 @@ def main():
         for rng, label in ((rt.RNG_PHILOX, "philox, sample ranges"), (rt.RNG_REFERENCE, "reference generator, tile rows")):
             res = {}
             for kl, key in ((one, "one_gpu"), (many, "n_gpus")):
-                kl.rng_mode, kl.seed = rng, 0
+                kl.rng_mode, kl.seed, kl.sample_streams = rng, 0, -1   # sample streams apply to Philox only
                 out = np.zeros(w * h * 3, np.float32)
                 kl.launch_Raytracing(out, *args)                       # uploads + warm-up
                 best = 1e9
