@@ -57,6 +57,7 @@ struct b200rt_ctx {
   int fast_ok = 1;
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
   int quorum = 20, refill_min = 8, tri_quorum = 4;
+  int carveout = -1;       // B200RT_CARVEOUT: k_trace's shared-memory carve-out (-1 driver's choice, 0 computed, else per cent)
   int max_trace_ctas = 0;  // B200RT_MAX_TRACE_CTAS: cap on resident k_trace CTAs per SM (0 = what fits)
   int compact_every = 8;   // B200RT_COMPACT_EVERY: wavefront iterations between two compactions of the path list
   std::vector<int32_t> tri_mat;  // for re-validating material edits
@@ -228,6 +229,14 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   }
   S.cull_abs = c->cull_abs;
   S.cmax = c->cmax;
+  {
+    // traversal-stack entry layout (rt_trace.cuh, LaneStack): 2^E above every culling limit, refs in the low bits
+    const int E = std::ilogb((1001.0f + c->cull_abs) * 1.01f) + 1;
+    S.st_bias = (uint32_t)(E - 32 + 127) << 23;
+    unsigned long long m = 1;
+    while (m < (unsigned long long)std::max(1, c->n_inner) * (unsigned long long)std::max(1, c->node_f4)) m <<= 1;
+    S.st_rmask = (uint32_t)(m - 1ull);
+  }
   S.stack_cap = effective_stack_cap(c, o);
   S.fast_ok = c->fast_ok;
   A->ibl = c->ibl_tex;
@@ -342,6 +351,17 @@ int prepare_trace_t(b200rt_ctx *c, WaveLaunch *w) {
   w->trace_smem = smem_bytes(c, SMEM);
   if (set_smem_attr(c, k, w->trace_smem)) return B200RT_ERR_CUDA;
   if (persistent_grid(c, k, w->trace_smem, &w->trace_grid)) return B200RT_ERR_CUDA;
+  if (c->carveout >= 0) {
+    // shared memory is carved out of the SM's L1: ask for what the resident CTAs need (+1 KB each, the system's share)
+    // and no more, so that the rest keeps caching nodes and triangles
+    int pct = c->carveout;
+    if (pct == 0) {
+      const size_t need = (size_t)(w->trace_grid / c->sm_count) * (w->trace_smem + 1024);
+      pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    }
+    if (pct > 100) pct = 100;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   if (c->max_trace_ctas > 0 && w->trace_grid > c->max_trace_ctas * c->sm_count) w->trace_grid = c->max_trace_ctas * c->sm_count;
   w->trace = k;
   return 0;
@@ -594,7 +614,7 @@ void borrow_scene(b200rt_ctx *p, b200rt_ctx *h) {
   }
   h->cull_abs = p->cull_abs; h->cmax = p->cmax; h->fast_ok = p->fast_ok;
   h->quorum = p->quorum; h->refill_min = p->refill_min; h->tri_quorum = p->tri_quorum;
-  h->max_trace_ctas = p->max_trace_ctas; h->compact_every = p->compact_every;
+  h->max_trace_ctas = p->max_trace_ctas; h->compact_every = p->compact_every; h->carveout = p->carveout;
   h->have_scene = p->have_scene;
   h->ibl_tex = p->ibl_tex; h->ibl_w = p->ibl_w; h->ibl_h = p->ibl_h; h->have_ibl = p->have_ibl;
   h->shared_epoch = p->scene_epoch;
@@ -753,6 +773,7 @@ int b200rt_create(int device, b200rt_ctx **out) {
   env_int("B200RT_REFILL_MIN", 1, 32, &c->refill_min);
   env_int("B200RT_TRI_QUORUM", 1, 32, &c->tri_quorum);
   env_int("B200RT_MAX_TRACE_CTAS", 1, 32, &c->max_trace_ctas);
+  env_int("B200RT_CARVEOUT", -1, 100, &c->carveout);
   env_int("B200RT_COMPACT_EVERY", 1, 1 << 20, &c->compact_every);
   auto bail = [&](const char *what, cudaError_t err) {
     fail(nullptr, B200RT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));

@@ -120,7 +120,7 @@ RT_DEV SceneView stage_scene(const KernelArgs &A, unsigned char *smem, size_t *u
 
 // dynamic shared memory after the staged scene: per-lane traversal stacks, then per-lane parked leaves
 __host__ __device__ inline size_t lane_smem_bytes(int stack_depth) {
-  return (size_t)kBlock * ((size_t)stack_depth * sizeof(float2) + (size_t)kParkCap * sizeof(uint32_t));
+  return (size_t)kBlock * ((size_t)stack_depth * sizeof(uint32_t) + (size_t)kParkCap * sizeof(uint32_t));
 }
 
 RT_DEV int work_to_pixel(const KernelArgs &A, unsigned int w) {
@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
   size_t used;
   SceneView S = stage_scene<SMEM>(A, smem, &used);
   LaneStack st;
-  st.base = reinterpret_cast<float2 *>(smem + used) + threadIdx.x;
+  st.base = reinterpret_cast<uint32_t *>(smem + used) + threadIdx.x;
   st.stride = kBlock;
-  uint32_t *parks = reinterpret_cast<uint32_t *>(smem + used + (size_t)kBlock * A.stack_depth * sizeof(float2)) + threadIdx.x;
+  uint32_t *parks = reinterpret_cast<uint32_t *>(smem + used + (size_t)kBlock * A.stack_depth * sizeof(uint32_t)) + threadIdx.x;
   const unsigned int lane = threadIdx.x & 31u;
   TraceCounters tc;
   tc.box_tests = 0; tc.tri_tests = 0;
@@ -595,9 +595,9 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
   size_t used;
   const SceneView S = stage_scene<SMEM>(A, smem, &used);
   LaneStack st;
-  st.base = reinterpret_cast<float2 *>(smem + used) + threadIdx.x;
+  st.base = reinterpret_cast<uint32_t *>(smem + used) + threadIdx.x;
   st.stride = kBlock;
-  uint32_t *parks = reinterpret_cast<uint32_t *>(smem + used + (size_t)kBlock * A.stack_depth * sizeof(float2)) + threadIdx.x;
+  uint32_t *parks = reinterpret_cast<uint32_t *>(smem + used + (size_t)kBlock * A.stack_depth * sizeof(uint32_t)) + threadIdx.x;
   const int *list = A.list[(iter + 1) & 1];
   unsigned int *wc = A.wc + iter;
   const unsigned int lane = threadIdx.x & 31u;
@@ -723,9 +723,9 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays(const __grid_constant__ K
   size_t used;
   SceneView S = stage_scene<SMEM>(A, smem, &used);
   LaneStack st;
-  st.base = reinterpret_cast<float2 *>(smem + used) + threadIdx.x;
+  st.base = reinterpret_cast<uint32_t *>(smem + used) + threadIdx.x;
   st.stride = kBlock;
-  uint32_t *parks = reinterpret_cast<uint32_t *>(smem + used + (size_t)kBlock * A.stack_depth * sizeof(float2)) + threadIdx.x;
+  uint32_t *parks = reinterpret_cast<uint32_t *>(smem + used + (size_t)kBlock * A.stack_depth * sizeof(uint32_t)) + threadIdx.x;
   TraceCounters tc;
   tc.box_tests = 0; tc.tri_tests = 0;
   unsigned int mism = 0;

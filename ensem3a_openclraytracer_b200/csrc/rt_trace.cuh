@@ -73,6 +73,8 @@ struct SceneView {
   float root_fc[3];         // node 0's box in the units of the node records (enclosing, like them)
   float root_hq[3];
   float cull_abs;           // absolute part of the culling margin (1e-3 x scene diagonal)
+  uint32_t st_bias;         // traversal-stack entries (LaneStack): binary32 bits of 2^(E - 32), where 2^E bounds every culling limit
+  uint32_t st_rmask;        //   and the mask of the low bits that hold the node ref
   float cmax;               // largest |coordinate| of any box plane, vertex or grid point
   int stack_cap;            // reference traversal
   int fast_ok;              // scene coordinates in the range the conservative test is proven for
@@ -351,12 +353,25 @@ __device__ __noinline__ Hit closest_hit_nodrop(const SceneView &S, v3 o, v3 d) {
 }
 
 // ---- fast traversal ---------------------------------------------------------------------------------------------
-// Per-lane stack in shared memory: entry e of lane l lives at stack[e * stride + l] (bank-conflict free),
-// each entry = (node ref, conservative entry distance).
+// Per-lane stack in shared memory: entry e of lane l lives at stack[e * stride + l] (bank-conflict free).
+// An entry is ONE word, (distance code | node ref): the ref (16-byte offset of an interior node) in the low bits that
+// SceneView::st_rmask covers, and above it the leading bits of the sub-tree's conservative entry distance, coded so
+// that the word order is the distance order:
+//     code(x) = (max(bits(x), st_bias) - st_bias) << 4,   bits() = the binary32 pattern read as a signed integer.
+// st_bias is the pattern of 2^(E-32) with 2^E above every culling limit (1001 + cull_abs), so a pushed distance
+// (always <= the limit of the moment) has bits(x) - st_bias < 2^28 and the shift loses nothing; negative distances and
+// everything below 2^(E-32) code as 0.  code() is monotone, hence  code(lo) > code(lim)  implies  lo > lim: a pop may
+// skip such an entry, exactly as the comparison of the full distances would, only a little less often (the code keeps
+// 5 exponent bits and 27 - log2(refs) mantissa bits; a bench-scene entry keeps 12).  Half the bytes of the round-1
+// (ref, distance) pair: the stacks of the resident CTAs are carved out of the SM's L1, which the node fetches need.
 struct LaneStack {
-  float2 *base;   // already offset to this thread
-  int stride;     // threads per block
+  uint32_t *base;   // already offset to this thread
+  int stride;       // threads per block
 };
+
+RT_DEV uint32_t stack_code(const SceneView &S, float x) {
+  return (uint32_t)(max(__float_as_int(x), (int)S.st_bias) - (int)S.st_bias) << 4;
+}
 
 // One traversal in flight.  Kept in registers; advanced one node at a time so that a warp can interleave
 // node steps, leaf tests and ray refills of its 32 lanes (k_trace), or simply looped (closest_hit_fast).
@@ -425,18 +440,19 @@ RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int
   if (both) { parks[pn * pstride] = (uint32_t)refFar; ++pn; }
   if (leafL || leafR) { parks[pn * pstride] = (uint32_t)(both ? refNear : (leafR ? refR : refL)); ++pn; }
   if (inL && inR) {
-    st.base[T.sp * st.stride] = make_float2(__int_as_float(refFar), rNear ? loL : loR);
+    st.base[T.sp * st.stride] = (stack_code(S, rNear ? loL : loR) & ~S.st_rmask) | (uint32_t)refFar;
     ++T.sp;
     T.cur = refNear;
   } else if (inL || inR) {
     T.cur = inL ? refL : refR;
   } else {
     T.cur = -1;
+    const uint32_t keep = stack_code(S, lim) | S.st_rmask;   // entries above this lie beyond the culling limit
     while (T.sp > 0) {
       --T.sp;
-      const float2 e = st.base[T.sp * st.stride];
-      if (!(e.y > lim)) {
-        T.cur = __float_as_int(e.x);
+      const uint32_t e = st.base[T.sp * st.stride];
+      if (e <= keep) {
+        T.cur = (int)(e & S.st_rmask);
         break;
       }
     }
