@@ -198,8 +198,8 @@ def repack_probe(vertex_p, vertex_n, face_data, n_materials, bvh):
         raise B200RTError(f"b200rt_repack_probe failed ({rc})")
     d = dict(n_inner=int(info[0]), node_f4=int(info[1]), depth=int(info[2]), ref_stack_need=int(info[3]),
              canonical=bool(info[4]), fast_ok=bool(info[5]), cmax=float(info[6]), cull_abs=float(info[7]),
-             grid_base=info[8:11].copy(), grid_pitch=info[11:14].copy(), root_fc=info[14:17].copy(),
-             root_hq=info[17:20].copy(), ranks=ranks, ms_tris=float(info[20]), ms_walk=float(info[21]), ms_nodes=float(info[22]))
+             grid_base=info[8:11].copy(), grid_pitch=info[11:14].copy(), root_qmin=info[14:17].copy(),
+             root_qmax=info[17:20].copy(), ranks=ranks, ms_tris=float(info[20]), ms_walk=float(info[21]), ms_nodes=float(info[22]), cull_depth=int(info[23]))
     return nodes, d
 
 

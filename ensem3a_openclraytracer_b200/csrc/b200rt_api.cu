@@ -49,10 +49,12 @@ struct b200rt_ctx {
   DevBuf d_nodes, d_tris, d_normals, d_tboxes, d_frames, d_mats, d_bvh9, d_leafcnt;
   int n_nodes9 = 0, n_inner = 0, n_tris = 0, n_mats = 0;
   int depth = 0, ref_stack_need = 0;
+  int cull_depth = 0;      // depth of the tree the node records hold (the culling tree, scene_repack.h)
   bool canonical = true;
   int root_ref = 0;
   int node_f4 = 2;
-  float grid_base[3] = {0, 0, 0}, grid_pitch[3] = {1, 1, 1}, root_fc[3] = {0.5f, 0.5f, 0.5f}, root_hq[3] = {0, 0, 0};
+  float grid_base[3] = {0, 0, 0}, grid_pitch[3] = {1, 1, 1};
+  uint32_t root_w[3] = {0x7fff0000u, 0x7fff0000u, 0x7fff0000u};
   float cull_abs = 0.0f, cmax = 0.0f;
   int fast_ok = 1;
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
@@ -92,6 +94,12 @@ struct b200rt_ctx {
 };
 
 namespace {
+
+// B200RT_CULL_TREE=0 keeps the caller's tree topology in the node records (development A/B; default: own tree)
+bool own_cull_tree() {
+  const char *q = getenv("B200RT_CULL_TREE");
+  return !(q && q[0] == '0');
+}
 
 int fail(b200rt_ctx *c, int code, const char *fmt, ...) {
   char buf[512];
@@ -200,7 +208,7 @@ bool use_smem_scene(const b200rt_ctx *c) { return c->node_f4 == 3; }
 
 // entries of the per-lane shared-memory traversal stack: the near-first walk holds at most one entry per level;
 // trees walked in reference order keep their stack in thread-local memory instead
-int stack_entries(const b200rt_ctx *c) { return c->canonical ? c->depth + 2 : 2; }
+int stack_entries(const b200rt_ctx *c) { return c->canonical ? c->cull_depth + 2 : 2; }
 
 size_t smem_bytes(const b200rt_ctx *c, bool smem_scene) {
   return lane_smem_bytes(stack_entries(c)) + (smem_scene ? scene_smem_bytes(c) : 0);
@@ -224,8 +232,7 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   for (int i = 0; i < 3; ++i) {
     S.grid_base[i] = c->grid_base[i];
     S.grid_pitch[i] = c->grid_pitch[i];
-    S.root_fc[i] = c->root_fc[i];
-    S.root_hq[i] = c->root_hq[i];
+    S.root_w[i] = c->root_w[i];
   }
   S.cull_abs = c->cull_abs;
   S.cmax = c->cmax;
@@ -606,11 +613,11 @@ void borrow_scene(b200rt_ctx *p, b200rt_ctx *h) {
   lend(h->d_light, p->d_light);
   h->n_light = p->n_light;
   h->n_nodes9 = p->n_nodes9; h->n_inner = p->n_inner; h->n_tris = p->n_tris; h->n_mats = p->n_mats;
-  h->node_f4 = p->node_f4; h->depth = p->depth; h->ref_stack_need = p->ref_stack_need; h->canonical = p->canonical;
+  h->node_f4 = p->node_f4; h->depth = p->depth; h->cull_depth = p->cull_depth; h->ref_stack_need = p->ref_stack_need; h->canonical = p->canonical;
   h->root_ref = p->root_ref;
   for (int k = 0; k < 3; ++k) {
     h->grid_base[k] = p->grid_base[k]; h->grid_pitch[k] = p->grid_pitch[k];
-    h->root_fc[k] = p->root_fc[k]; h->root_hq[k] = p->root_hq[k];
+    h->root_w[k] = p->root_w[k];
   }
   h->cull_abs = p->cull_abs; h->cmax = p->cmax; h->fast_ok = p->fast_ok;
   h->quorum = p->quorum; h->refill_min = p->refill_min; h->tri_quorum = p->tri_quorum;
@@ -924,14 +931,14 @@ int upload_scene(b200rt_ctx *c, const Repacked &R, const SceneArgs &a, uint64_t 
   c->n_tris = n_tris;
   c->node_f4 = R.node_f4;
   c->depth = R.depth;
+  c->cull_depth = R.cull_depth;
   c->ref_stack_need = R.ref_stack_need;
   c->canonical = R.canonical;
   c->root_ref = R.root_ref;
   for (int k = 0; k < 3; ++k) {
     c->grid_base[k] = R.grid_base[k];
     c->grid_pitch[k] = R.grid_pitch[k];
-    c->root_fc[k] = R.root_fc[k];
-    c->root_hq[k] = R.root_hq[k];
+    c->root_w[k] = R.root_w[k];
   }
   c->cull_abs = R.cull_abs;
   c->cmax = R.cmax;
@@ -972,7 +979,7 @@ int b200rt_set_scene(b200rt_ctx *c, const float *vp, int64_t n_vp, const float *
   } else {
     Repacked R;
     std::string msg;
-    rc = repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_mat / 6, bvh, n_bvh, &R, &msg);
+    rc = repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_mat / 6, bvh, n_bvh, &R, &msg, own_cull_tree());
     if (rc) {
       c->have_scene = false;   // as before an upload: the context describes no scene after a rejected one
       c->have_scene_cached = false;
@@ -1464,7 +1471,7 @@ int b200rt_multi_set_scene(b200rt_multi *m, const float *vp, int64_t n_vp, const
   Repacked R;
   if (!all_cached) {  // validated and repacked once, uploaded to every GPU
     std::string msg;
-    rc = repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_mat / 6, bvh, n_bvh, &R, &msg);
+    rc = repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_mat / 6, bvh, n_bvh, &R, &msg, own_cull_tree());
     if (rc) {
       for (b200rt_ctx *c : m->ctx) { c->have_scene = false; c->have_scene_cached = false; c->scene_hash = 0; }
       return mfail(m, rc, "%s", msg.c_str());

@@ -607,6 +607,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
   T.best.tri = -1; T.best.k = 1000.0f; T.best_rank = 0x7fffffff; T.lim = 0.0f; T.cur = -1; T.sp = 0;
   T.o = mk3(0, 0, 0); T.d = mk3(1, 1, 1);
   T.Q.A = mk3(1, 1, 1); T.Q.Bn = mk3(0, 0, 0); T.Q.Bf = mk3(0, 0, 0);
+  for (int a = 0; a < 3; ++a) { T.Q.sn[a] = kSelMin; T.Q.sf[a] = kSelMax; }
   int pn = 0;         // parked leaves of this lane
   int path = -1;      // path whose ray this lane is tracing
   unsigned int c_next = 0, c_end = 0;  // the warp's claimed chunk of the list (uniform)

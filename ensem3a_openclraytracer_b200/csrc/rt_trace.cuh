@@ -39,18 +39,20 @@ namespace b200rt {
 // ---- repacked scene -------------------------------------------------------------------------------
 // node (32 B = 8 words, ONE 256-bit load per visit; 32 B apart in global memory, 48 B apart when the scene is
 // staged in shared memory so that lanes reading different nodes spread over all bank groups), interior nodes only,
-// root = 0.  A record holds the boxes of BOTH children, quantised onto a 2^15 grid spanning the root box:
-//   w0 = Lcx|Lcy   w1 = Lcz|Rcx   w2 = Rcy|Rcz      centre, 15-bit grid index q per axis (hi|lo 16-bit halves)
-//   w3 = Lhx|Lhy   w4 = Lhz|Rhx   w5 = Rhy|Rhz      half extent / grid pitch, upper 16 bits of a binary32 (rounded up)
-//   w6 = refL      w7 = refR                        ref >= 0: float4 offset of an interior node (index x node_f4),
+// root = 0.  A record holds the boxes of BOTH children as planes on a 2^15 grid spanning the root box:
+//   w0 = L.x   w1 = L.y   w2 = L.z   w3 = R.x   w4 = R.y   w5 = R.z     one axis of one child per word:
+//                                                   grid index of the max plane << 16 | grid index of the min plane
+//   w6 = refL  w7 = refR                            ref >= 0: float4 offset of an interior node (index x node_f4),
 //                                                   ref < 0: leaf of triangle ~ref
-// Decoding costs one instruction per value and no conversion: PRMT places q in mantissa bits 22..8 under the
-// exponent of 0.5, giving the binary32 fc = 0.5 + q / 65536 exactly; `w & 0xffff0000` / `w << 16` are the half
-// extents.  In real arithmetic the decoded box is  c = grid_base + fc * grid_pitch,  h = hq * grid_pitch  per axis,
-// and b200rt_set_scene chooses q and hq so that [c - h, c + h] ENCLOSES the child's exact float32 [min, max] (checked
-// there in binary64).  These boxes only cull; exactness lives in the leaf boxes of `tboxes` and in the as-is array
-// `bvh9`.  Against the round-1 record (two boxes as 12 floats, 64 B, two 256-bit loads) this halves the L1 /
-// L2 / HBM bytes and the L1 wavefronts of every node visit; ncu had the L1TEX data pipe of k_trace at 83 %.
+// Decoding is ONE instruction per plane and no conversion: PRMT drops the 15-bit index q into mantissa bits 22..8 under
+// the exponent of 0.5, giving the binary32 fq = 0.5 + q / 65536 exactly; in real arithmetic the plane lies at
+// grid_base + fq * grid_pitch.  Which half of the word a ray enters through (its NEAR plane) depends only on the sign of
+// its direction on that axis, so every ray carries the two PRMT selectors per axis and a box costs six FMAs:
+//     near = fma(fq_near, A, Bn),   far = fma(fq_far, A, Bf)          (slab_cons below)
+// b200rt_set_scene chooses the indices so that [min plane, max plane] ENCLOSES the child's exact float32 [min, max]
+// (checked there in binary64).  These boxes only cull; exactness lives in the leaf boxes of `tboxes` and in the as-is
+// array `bvh9`.  History: round 1 read two boxes as 12 floats (64 B, two 256-bit loads; ncu had the L1TEX data pipe
+// of k_trace at 83 %); the first 32-byte record held centre / half-extent pairs and cost twelve FMAs per box.
 // triangle (48 B, 3 x float4):
 //   t0 = A.x A.y A.z e1.x     t1 = e1.y e1.z e2.x e2.y     t2 = e2.z mat rank -   (mat, rank int bits)
 //   with e1 = B - A, e2 = C - A rounded exactly as MathLib.cl:129-130 rounds them.
@@ -70,8 +72,7 @@ struct SceneView {
   int root_ref;             // ~tri when the whole tree is one leaf
   float grid_base[3];       // decoded centre = grid_base + fc * grid_pitch   (fc in [0.5, 1))
   float grid_pitch[3];
-  float root_fc[3];         // node 0's box in the units of the node records (enclosing, like them)
-  float root_hq[3];
+  uint32_t root_w[3];       // node 0's box, one word per axis in the format of the node records (enclosing, like them)
   float cull_abs;           // absolute part of the culling margin (1e-3 x scene diagonal)
   uint32_t st_bias;         // traversal-stack entries (LaneStack): binary32 bits of 2^(E - 32), where 2^E bounds every culling limit
   uint32_t st_rmask;        //   and the mask of the low bits that hold the node ref
@@ -109,10 +110,9 @@ RT_DEV void ld_node(const uint4 *p, uint4 &a, uint4 &b) {
   }
 }
 
-RT_DEV float fc_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3f000000u, 0x7324)); }  // 0.5 + (w >> 16) / 65536
-RT_DEV float fc_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3f000000u, 0x7104)); }  // 0.5 + (w & 0xffff) / 65536
-RT_DEV float hq_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-RT_DEV float hq_lo(uint32_t w) { return __uint_as_float(w << 16); }
+constexpr uint32_t kSelMax = 0x7324u;   // PRMT selector: 0.5 + (w >> 16) / 65536      (the max plane of a node word)
+constexpr uint32_t kSelMin = 0x7104u;   //                0.5 + (w & 0xffff) / 65536   (the min plane)
+RT_DEV float plane_fq(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x3f000000u, sel)); }
 
 // ---- exact slab test, MathLib.cl:169-188 --------------------------------------------------------------
 // x / d, IEEE round-to-nearest.  The hardware division routine sends a zero numerator to its out-of-line slow path
@@ -140,24 +140,25 @@ RT_DEV bool slab_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, f
 }
 
 // ---- conservative slab test ----------------------------------------------------------------------------
-// A box is held as (fc, hq) per axis, meaning centre c = base + fc * pitch and half extent h = hq * pitch in real
-// arithmetic, with [c - h, c + h] enclosing the exact [min, max].  Per ray and axis: r = RN(1/d),
+// A box is held per axis as two grid planes fq_min <= fq_max, a plane lying at x = base + fq * pitch in real arithmetic,
+// with [x_min, x_max] enclosing the exact [min, max].  Per ray and axis: r = RN(1/d),
 //     A = RN(pitch * r),   B = RN(RN(base - o) * r),   Bn = B - m,   Bf = B + m,
-//     near = fma(-hq, |A|, fma(fc, A, Bn)),   far = fma(+hq, |A|, fma(fc, A, Bf))
-// — FMAs only, no per-axis min / max because |A| orders the two planes.  The three `near` and the three `far` values
-// are reduced with one 3-input max / min each to lo and hi.
+//     near = fma(fq_near, A, Bn),   far = fma(fq_far, A, Bf),      fq_near = A >= 0 ? fq_min : fq_max, fq_far the other
+// — one FMA per plane, no per-axis min / max because the sign of A orders the two planes (the ray carries the PRMT
+// selectors that pick them out of the node word).  The three `near` and the three `far` values are reduced with one
+// 3-input max / min each to lo and hi.
 // Error budget per axis, in units of u (cmax + |o|) |r| with u = 2^-24.  b200rt_set_scene makes cmax bound every
-// |box plane|, |vertex coordinate|, |base| and |base + pitch|, hence pitch <= 2 cmax and |c| <= cmax for every decoded
-// centre.  A = RN(pitch·r), scaled by fc < 1: 2.  B: one rounding of base - o (<= cmax + |o|) and one of the product: 2.
-// Bn / Bf: 1.  r against 1/d: 1.  Inner FMA: 1 (|result| <= (cmax + |o|)|r| + m).  Outer FMA: 2 (|result| <= (2 cmax + |o|)|r| + m).
-// hq·|A| against h·|r|, where hq·pitch >= h exactly and |A| >= pitch |r| (1 - 2u): 2.  Together 11.  The reference's own
+// |box plane|, |vertex coordinate|, |base| and |base + pitch|, hence pitch <= 2 cmax and |x| <= cmax for every decoded
+// plane.  A = RN(pitch·r), scaled by fq < 1: 2.  B: one rounding of base - o (<= cmax + |o|) and one of the product: 2.
+// Bn / Bf: 1.  r against 1/d: 1.  The FMA: 2 (|result| <= (2 cmax + |o|)|r| + m).  Together 8.  The reference's own
 // t = RN(RN(p - o) / d) is within 2 of the real (p - o)/d.  The margin, PER AXIS (a ray with one tiny direction
 // component must not lose the culling of the other two axes),
-//     m = 2^-18 (cmax + |o|) |r|        (= 64 units, five times the sum of 13),
+//     m = 2^-18 (cmax + |o|) |r|        (= 64 units, six times the sum of 10),
 // gives  lo <= tmin_exact  and  hi >= tmax_exact: the box certainly fails the reference's test when hi < lo.
 // Valid while every |d| component lies in [2^-40, 2^40] and |o|, cmax <= 2^40 (no overflow, no denormal r).
 struct RayFast {
   v3 A, Bn, Bf;
+  uint32_t sn[3], sf[3];   // PRMT selectors of the near / far plane per axis (kSelMin / kSelMax)
 };
 
 RT_DEV bool comp_ok(float d) {
@@ -185,8 +186,11 @@ RT_DEV bool ray_is_fast(const SceneView &S, v3 o) {
 // Either way the reference can only be stricter, so the traversal still visits a superset of the candidates;
 // validate_chain then decides whether the winner is one.
 RT_DEV void rayfast_axis(float o, float d, float cmax, float cull_abs, float base, float pitch, float *A, float *Bn,
-                         float *Bf) {
+                         float *Bf, uint32_t *sn, uint32_t *sf) {
   const float a = fabsf(d);
+  const bool neg = (__float_as_uint(d) >> 31) != 0u;   // the sign of A = pitch * r (pitch > 0)
+  *sn = neg ? kSelMax : kSelMin;
+  *sf = neg ? kSelMin : kSelMax;
   float rr, extra = 0.0f;
   if (a >= 9.094947017729282e-13f /* 2^-40 */ && a <= 1.099511627776e12f /* 2^40 */) {
     rr = __frcp_rn(d);
@@ -208,22 +212,21 @@ RT_DEV void rayfast_axis(float o, float d, float cmax, float cull_abs, float bas
 
 RT_DEV RayFast make_rayfast(const SceneView &S, v3 o, v3 d) {
   RayFast Q;
-  rayfast_axis(o.x, d.x, S.cmax, S.cull_abs, S.grid_base[0], S.grid_pitch[0], &Q.A.x, &Q.Bn.x, &Q.Bf.x);
-  rayfast_axis(o.y, d.y, S.cmax, S.cull_abs, S.grid_base[1], S.grid_pitch[1], &Q.A.y, &Q.Bn.y, &Q.Bf.y);
-  rayfast_axis(o.z, d.z, S.cmax, S.cull_abs, S.grid_base[2], S.grid_pitch[2], &Q.A.z, &Q.Bn.z, &Q.Bf.z);
+  rayfast_axis(o.x, d.x, S.cmax, S.cull_abs, S.grid_base[0], S.grid_pitch[0], &Q.A.x, &Q.Bn.x, &Q.Bf.x, &Q.sn[0], &Q.sf[0]);
+  rayfast_axis(o.y, d.y, S.cmax, S.cull_abs, S.grid_base[1], S.grid_pitch[1], &Q.A.y, &Q.Bn.y, &Q.Bf.y, &Q.sn[1], &Q.sf[1]);
+  rayfast_axis(o.z, d.z, S.cmax, S.cull_abs, S.grid_base[2], S.grid_pitch[2], &Q.A.z, &Q.Bn.z, &Q.Bf.z, &Q.sn[2], &Q.sf[2]);
   return Q;
 }
 
-// lo <= tmin_exact and hi >= tmax_exact of the box enclosed by (fc, hq); the box certainly fails when hi < lo
-RT_DEV void slab_cons(const RayFast &Q, float fcx, float fcy, float fcz, float hx, float hy, float hz, float *lo,
-                      float *hi) {
-  const float ax = fabsf(Q.A.x), ay = fabsf(Q.A.y), az = fabsf(Q.A.z);
-  const float nx = __fmaf_rn(-hx, ax, __fmaf_rn(fcx, Q.A.x, Q.Bn.x));
-  const float ny = __fmaf_rn(-hy, ay, __fmaf_rn(fcy, Q.A.y, Q.Bn.y));
-  const float nz = __fmaf_rn(-hz, az, __fmaf_rn(fcz, Q.A.z, Q.Bn.z));
-  const float fx = __fmaf_rn(hx, ax, __fmaf_rn(fcx, Q.A.x, Q.Bf.x));
-  const float fy = __fmaf_rn(hy, ay, __fmaf_rn(fcy, Q.A.y, Q.Bf.y));
-  const float fz = __fmaf_rn(hz, az, __fmaf_rn(fcz, Q.A.z, Q.Bf.z));
+// lo <= tmin_exact and hi >= tmax_exact of the box whose three axis words are (wx, wy, wz); the box certainly fails
+// when hi < lo
+RT_DEV void slab_cons(const RayFast &Q, uint32_t wx, uint32_t wy, uint32_t wz, float *lo, float *hi) {
+  const float nx = __fmaf_rn(plane_fq(wx, Q.sn[0]), Q.A.x, Q.Bn.x);
+  const float ny = __fmaf_rn(plane_fq(wy, Q.sn[1]), Q.A.y, Q.Bn.y);
+  const float nz = __fmaf_rn(plane_fq(wz, Q.sn[2]), Q.A.z, Q.Bn.z);
+  const float fx = __fmaf_rn(plane_fq(wx, Q.sf[0]), Q.A.x, Q.Bf.x);
+  const float fy = __fmaf_rn(plane_fq(wy, Q.sf[1]), Q.A.y, Q.Bf.y);
+  const float fz = __fmaf_rn(plane_fq(wz, Q.sf[2]), Q.A.z, Q.Bf.z);
   *lo = fmaxf(fmaxf(nx, ny), nz);
   *hi = fminf(fminf(fx, fy), fz);
 }
@@ -405,7 +408,7 @@ RT_DEV void trav_begin(const SceneView &S, Trav &T, v3 o, v3 d, int &pn, uint32_
   T.sp = 0;
   float lo, hi;
   if (STATS) cnt->box_tests++;
-  slab_cons(T.Q, S.root_fc[0], S.root_fc[1], S.root_fc[2], S.root_hq[0], S.root_hq[1], S.root_hq[2], &lo, &hi);
+  slab_cons(T.Q, S.root_w[0], S.root_w[1], S.root_w[2], &lo, &hi);
   const bool go = hi >= lo;
   T.cur = go ? 0 : -1;
   if (go && S.root_ref < 0) {
@@ -425,8 +428,8 @@ RT_DEV void trav_step(const SceneView &S, Trav &T, int &pn, uint32_t *parks, int
   const int refL = (int)wb.z, refR = (int)wb.w;
   float loL, hiL, loR, hiR;
   if (STATS) cnt->box_tests += 2;
-  slab_cons(T.Q, fc_hi(wa.x), fc_lo(wa.x), fc_hi(wa.y), hq_hi(wa.w), hq_lo(wa.w), hq_hi(wb.x), &loL, &hiL);
-  slab_cons(T.Q, fc_lo(wa.y), fc_hi(wa.z), fc_lo(wa.z), hq_lo(wb.x), hq_hi(wb.y), hq_lo(wb.y), &loR, &hiR);
+  slab_cons(T.Q, wa.x, wa.y, wa.z, &loL, &hiL);
+  slab_cons(T.Q, wa.w, wb.x, wb.y, &loR, &hiR);
   const float lim = T.lim;
   const float behind = -S.cull_abs;
   const bool goL = hiL >= loL && !(loL > lim) && !(hiL < behind);

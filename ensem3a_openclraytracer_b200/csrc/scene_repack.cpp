@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/b200rt.h"
@@ -36,42 +37,33 @@ uint32_t as_u32(float f) {
   return u;
 }
 
-// smallest value with only the upper 16 bits of a binary32 set that is >= x (x >= 0, finite)
-float bf16_up(double x) {
-  float f = (float)x;
-  if ((double)f < x) f = std::nextafterf(f, INFINITY);
-  uint32_t u = as_u32(f);
-  if (u & 0xffffu) u = (u + 0x10000u) & 0xffff0000u;
-  return as_float(u);
-}
-
-// The grid of one axis: decoded centre = base + fc * pitch, fc = 0.5 + q / 65536, q in [0, 32767].
+// The grid of one axis: plane q lies at base + fq * pitch, fq = 0.5 + q / 65536, q in [0, 32767].
 struct Axis {
   float base, pitch;
 };
 
-// (q, hq) whose decoded box encloses [mn, mx] in real arithmetic.  binary64 throughout: fc * pitch is exact (16 x 24
-// bits), the sum with base rounds once (relative 2^-53), and `slack` covers that rounding many times over.
-void quantise(const Axis &g, float mn, float mx, uint32_t *q_out, float *hq_out) {
+double plane_at(const Axis &g, int q) { return (double)g.base + (0.5 + q / 65536.0) * (double)g.pitch; }
+
+// Grid planes (q_min, q_max) that enclose [mn, mx] in real arithmetic, packed as a node-record word.  binary64
+// throughout: fq * pitch is exact (16 x 24 bits), the sum with base rounds once (relative 2^-53), and `slack` covers
+// that rounding many times over.  Returns false when the grid does not reach that far (a box outside the root box).
+bool quantise(const Axis &g, float mn, float mx, uint32_t *w_out) {
   const double base = g.base, pitch = g.pitch;
-  const double mid = 0.5 * ((double)mn + (double)mx);
-  double qf = std::floor(((mid - base) / pitch - 0.5) * 65536.0 + 0.5);
-  if (!(qf >= 0.0)) qf = 0.0;
-  if (qf > 32767.0) qf = 32767.0;
-  const double fc = 0.5 + qf / 65536.0;
-  const double c = base + fc * pitch;
   const double slack = (std::fabs(base) + pitch) * 0x1p-48;
-  const double need = std::max(c - (double)mn, (double)mx - c) + slack;
-  float hq = bf16_up((need / pitch) * (1.0 + 0x1p-40));
-  while ((double)hq * pitch < need) hq = as_float(as_u32(hq) + 0x10000u);
-  *q_out = (uint32_t)qf;
-  *hq_out = hq;
+  double fl = std::floor((((double)mn - base) / pitch - 0.5) * 65536.0);
+  double fh = std::ceil((((double)mx - base) / pitch - 0.5) * 65536.0);
+  int ql = !(fl >= 0.0) ? 0 : (fl > 32767.0 ? 32767 : (int)fl);
+  int qh = !(fh >= 0.0) ? 0 : (fh > 32767.0 ? 32767 : (int)fh);
+  while (ql > 0 && plane_at(g, ql) > (double)mn - slack) --ql;
+  while (qh < 32767 && plane_at(g, qh) < (double)mx + slack) ++qh;
+  *w_out = ((uint32_t)qh << 16) | (uint32_t)ql;
+  return plane_at(g, ql) <= (double)mn - slack && plane_at(g, qh) >= (double)mx + slack;
 }
 
 }  // namespace
 
 int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const int32_t *face, int64_t n_face,
-                 int64_t n_materials, const float *bvh, int64_t n_bvh, Repacked *out, std::string *err) {
+                 int64_t n_materials, const float *bvh, int64_t n_bvh, Repacked *out, std::string *err, bool own_tree) {
   Repacked &R = *out;
   const int n_nodes = (int)(n_bvh / 9), n_tris = (int)(n_face / 10);
   const int nvp = (int)(n_vp / 3), nvn = (int)(n_vn / 3), nm = (int)n_materials;
@@ -319,12 +311,21 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
     return B200RT_ERR_INVALID;
   }
   R.depth = depth;
+  R.cull_depth = depth;
+  R.cull_tree = 0;
   R.ref_stack_need = (int)max_stack;
   if (R.ref_stack_need > kRefStackMax) canonical = false;  // closest_hit_nodrop's thread-local stack
-  // a pathologically deep tree would not leave room for the per-lane stacks in shared memory
-  if (lane_smem_bytes_host(depth + 2) > kLaneSmemMax) canonical = false;
   double t2 = now_ms();
   R.ms_walk = t2 - t1;
+
+  // ---- the culling tree: built here over the leaf boxes (cull_tree.cpp), or the caller's topology ------------------
+  std::vector<CullNode> cull;
+  if (canonical && own_tree && T(0) == -1) {
+    build_cull_tree(R.tboxes.data(), n_tris, &cull, &R.cull_depth);
+    R.cull_tree = 1;
+  }
+  // a pathologically deep tree would not leave room for the per-lane stacks in shared memory
+  if (lane_smem_bytes_host(R.cull_depth + 2) > kLaneSmemMax) canonical = false;
 
   // ---- grid of the quantised node boxes ------------------------------------------------------------------
   Axis grid[3];
@@ -337,21 +338,23 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
     if (ext_max == 0.0) ext_max = std::max((double)cmax, 1e-30) * 0x1p-12;
     for (int k = 0; k < 3; ++k) {
       const double e = std::max(ext[k], ext_max / 256.0);   // bounded anisotropy: a flat scene keeps a usable pitch
-      float pitch = (float)(e * (65536.0 / 32767.0) * (1.0 + 0x1p-20));
-      if (!(pitch > 0.0f) || !std::isfinite(pitch)) pitch = 1.0f;
-      float base = (float)((double)bvh[2 + k] - 0.5 * (double)pitch);
-      if ((double)base > (double)bvh[2 + k] - 0.5 * (double)pitch) base = std::nextafterf(base, -INFINITY);
-      if (!std::isfinite(base)) base = 0.0f;
-      grid[k] = Axis{base, pitch};
-      R.grid_base[k] = base;
-      R.grid_pitch[k] = pitch;
-      const float hi = std::fabs(base + pitch) * (1.0f + 0x1p-20f), lo = std::fabs(base);
+      // plane 0 just below the root's min, plane 32767 just above its max; the span is widened until both hold with the
+      // float32 roundings of base and pitch (a scene far from the origin relative to its size needs several ulps)
+      double widen = 0x1p-20;
+      for (int attempt = 0;; ++attempt) {
+        float pitch = (float)(e * (65536.0 / 32767.0) * (1.0 + 8.0 * widen));
+        if (!(pitch > 0.0f) || !std::isfinite(pitch)) pitch = 1.0f;
+        float base = (float)((double)bvh[2 + k] - 2.0 * widen * e - 0.5 * (double)pitch);
+        base = std::nextafterf(base, -INFINITY);
+        if (!std::isfinite(base)) base = 0.0f;
+        grid[k] = Axis{base, pitch};
+        if (quantise(grid[k], bvh[2 + k], bvh[5 + k], &R.root_w[k]) || attempt == 24) break;
+        widen *= 4.0;
+      }
+      R.grid_base[k] = grid[k].base;
+      R.grid_pitch[k] = grid[k].pitch;
+      const float hi = std::fabs(grid[k].base + grid[k].pitch) * (1.0f + 0x1p-20f), lo = std::fabs(grid[k].base);
       cmax = std::max(cmax, std::max(hi, lo));
-      uint32_t q;
-      float hq;
-      quantise(grid[k], bvh[2 + k], bvh[5 + k], &q, &hq);
-      R.root_fc[k] = 0.5f + (float)q / 65536.0f;
-      R.root_hq[k] = hq;
     }
     const float dx = bvh[5] - bvh[2], dy = bvh[6] - bvh[3], dz = bvh[7] - bvh[4];
     R.cull_abs = 1e-3f * std::sqrt(dx * dx + dy * dy + dz * dz);
@@ -374,6 +377,7 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
       R.root_ref = ~T(0);
     } else {
       std::vector<int> order;
+      if (!R.cull_tree) {
       order.reserve((size_t)n_nodes / 2 + 1);
       order.push_back(0);
       inner_id[0] = 0;
@@ -402,40 +406,47 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
             if (T(ch[k]) == -1) todo.push_back(ch[k]);
         }
       }
-      const int n_inner = (int)order.size();
+      }
+      const int n_inner = R.cull_tree ? (int)cull.size() : (int)order.size();
       R.n_inner = n_inner;
       // small scenes are staged in shared memory with 48-byte node spacing (SceneView::node_f4)
       const int nf4 = ((size_t)n_inner * 48 + (size_t)n_tris * 48 <= kSmemSceneMax) ? 3 : 2;
       R.node_f4 = nf4;
       R.nodes.resize((size_t)n_inner * nf4);
-#pragma omp parallel for schedule(static)
+      int outside = 0;   // a box the grid over the root box cannot enclose
+#pragma omp parallel for schedule(static) reduction(| : outside)
       for (int q = 0; q < n_inner; ++q) {
-        const int cur = order[q];
-        const int l = L(cur), r = Rc(cur);
-        const float *bl = bvh + 9 * (size_t)l, *br = bvh + 9 * (size_t)r;
-        // interior refs are 16-byte offsets into the node array (index x 16-byte units per node)
-        const int32_t refl = T(l) != -1 ? ~T(l) : (int32_t)(inner_id[l] * nf4);
-        const int32_t refr = T(r) != -1 ? ~T(r) : (int32_t)(inner_id[r] * nf4);
-        uint32_t ql[3], qr[3];
-        float hl[3], hr[3];
-        for (int k = 0; k < 3; ++k) {
-          quantise(grid[k], bl[2 + k], bl[5 + k], &ql[k], &hl[k]);
-          quantise(grid[k], br[2 + k], br[5 + k], &qr[k], &hr[k]);
+        const float *bl, *br;   // min.xyz, max.xyz of the two children
+        int32_t refl, refr;     // interior refs are 16-byte offsets into the node array (index x 16-byte units per node)
+        if (R.cull_tree) {
+          const CullNode &N = cull[q];
+          bl = N.box[0]; br = N.box[1];
+          refl = N.ref[0] < 0 ? N.ref[0] : N.ref[0] * nf4;
+          refr = N.ref[1] < 0 ? N.ref[1] : N.ref[1] * nf4;
+        } else {
+          const int cur = order[q];
+          const int l = L(cur), r = Rc(cur);
+          bl = bvh + 9 * (size_t)l + 2; br = bvh + 9 * (size_t)r + 2;
+          refl = T(l) != -1 ? ~T(l) : (int32_t)(inner_id[l] * nf4);
+          refr = T(r) != -1 ? ~T(r) : (int32_t)(inner_id[r] * nf4);
         }
-        auto hi16 = [](float f) { return as_u32(f) & 0xffff0000u; };
-        auto lo16 = [](float f) { return as_u32(f) >> 16; };
+        uint32_t wl[3], wr[3];
+        for (int k = 0; k < 3; ++k)
+          if (!quantise(grid[k], bl[k], bl[3 + k], &wl[k]) || !quantise(grid[k], br[k], br[3 + k], &wr[k])) outside |= 1;
         Repacked::u4 a, b;
-        a.x = (ql[0] << 16) | ql[1];
-        a.y = (ql[2] << 16) | qr[0];
-        a.z = (qr[1] << 16) | qr[2];
-        a.w = hi16(hl[0]) | lo16(hl[1]);
-        b.x = hi16(hl[2]) | lo16(hr[0]);
-        b.y = hi16(hr[1]) | lo16(hr[2]);
+        a.x = wl[0]; a.y = wl[1]; a.z = wl[2]; a.w = wr[0];
+        b.x = wr[1]; b.y = wr[2];
         b.z = (uint32_t)refl;
         b.w = (uint32_t)refr;
         R.nodes[(size_t)nf4 * q + 0] = a;
         R.nodes[(size_t)nf4 * q + 1] = b;
         if (nf4 == 3) R.nodes[(size_t)nf4 * q + 2] = Repacked::u4{0, 0, 0, 0};
+      }
+      if (outside) {   // cannot happen for nested boxes; such a tree is walked in reference order
+        R.canonical = false;
+        R.nodes.clear();
+        R.n_inner = 0;
+        R.node_f4 = 2;
       }
     }
   }
@@ -453,14 +464,16 @@ extern "C" int b200rt_repack_probe(const float *vp, int64_t n_vp, const float *v
     return B200RT_ERR_INVALID;
   b200rt::Repacked R;
   std::string msg;
-  int rc = b200rt::repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_materials, bvh, n_bvh, &R, &msg);
+  const char *own = getenv("B200RT_CULL_TREE");
+  int rc = b200rt::repack_scene(vp, n_vp, vn, n_vn, face, n_face, n_materials, bvh, n_bvh, &R, &msg, !(own && own[0] == '0'));
   if (rc) return rc;
   info[0] = (float)R.n_inner; info[1] = (float)R.node_f4; info[2] = (float)R.depth; info[3] = (float)R.ref_stack_need;
   info[4] = R.canonical ? 1.0f : 0.0f; info[5] = (float)R.fast_ok; info[6] = R.cmax; info[7] = R.cull_abs;
   for (int k = 0; k < 3; ++k) {
-    info[8 + k] = R.grid_base[k]; info[11 + k] = R.grid_pitch[k]; info[14 + k] = R.root_fc[k]; info[17 + k] = R.root_hq[k];
+    info[8 + k] = R.grid_base[k]; info[11 + k] = R.grid_pitch[k];
+    info[14 + k] = (float)(R.root_w[k] & 0xffffu); info[17 + k] = (float)(R.root_w[k] >> 16);   // root box: min / max plane index
   }
-  info[20] = (float)R.ms_tris; info[21] = (float)R.ms_walk; info[22] = (float)R.ms_nodes; info[23] = 0.0f;
+  info[20] = (float)R.ms_tris; info[21] = (float)R.ms_walk; info[22] = (float)R.ms_nodes; info[23] = (float)R.cull_depth;
   if (rank_out)
     for (int t = 0; t < R.n_tris; ++t) memcpy(&rank_out[t], &R.tris[3 * (size_t)t + 2].z, 4);
   if (nodes_out) {

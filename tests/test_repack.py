@@ -10,22 +10,31 @@ from ensem3a_openclraytracer_b200._capi import B200RTError
 from tests import fixtures
 
 
-def probe(sc, bvh=None):
-    return _capi.repack_probe(sc["V_p"], sc["V_n"], sc["faceData"], max(1, len(sc["materialData"]) // 6),
-                              sc["BVH"] if bvh is None else bvh)
+def probe(sc, bvh=None, own_tree=False):
+    """own_tree=False: the node records keep the caller's topology (B200RT_CULL_TREE=0), which is what the checks
+    against BVH.py's array below compare; own_tree=True: the culling tree of csrc/cull_tree.cpp (the default)."""
+    import os
+    old = os.environ.get("B200RT_CULL_TREE")
+    os.environ["B200RT_CULL_TREE"] = "1" if own_tree else "0"
+    try:
+        return _capi.repack_probe(sc["V_p"], sc["V_n"], sc["faceData"], max(1, len(sc["materialData"]) // 6),
+                                  sc["BVH"] if bvh is None else bvh)
+    finally:
+        if old is None:
+            del os.environ["B200RT_CULL_TREE"]
+        else:
+            os.environ["B200RT_CULL_TREE"] = old
 
 
 def decode(nodes, info):
-    """(centre, half) float64 arrays [n_inner, 2 children, 3 axes] from the packed records (rt_trace.cuh)."""
-    w = nodes.astype(np.uint64)
-    hi, lo = (lambda x: x >> 16), (lambda x: x & 0xffff)
-    q = np.stack([np.stack([hi(w[:, 0]), lo(w[:, 0]), hi(w[:, 1])], 1), np.stack([lo(w[:, 1]), hi(w[:, 2]), lo(w[:, 2])], 1)], 1)
-    assert q.max() <= 32767
-    fbits = lambda x: x.astype(np.uint32).view(np.float32).astype(np.float64)
-    hq = np.stack([np.stack([fbits(w[:, 3] & 0xffff0000), fbits((w[:, 3] << 16) & 0xffffffff), fbits(w[:, 4] & 0xffff0000)], 1),
-                   np.stack([fbits((w[:, 4] << 16) & 0xffffffff), fbits(w[:, 5] & 0xffff0000), fbits((w[:, 5] << 16) & 0xffffffff)], 1)], 1)
+    """(min plane, max plane) float64 arrays [n_inner, 2 children, 3 axes] from the packed records (rt_trace.cuh):
+    one word per child and axis, grid index of the max plane << 16 | grid index of the min plane."""
+    w = nodes[:, :6].astype(np.uint64).reshape(-1, 2, 3)
+    qmax, qmin = w >> 16, w & 0xffff
+    assert qmax.max() <= 32767 and (qmin <= qmax).all()
     base, pitch = info["grid_base"].astype(np.float64), info["grid_pitch"].astype(np.float64)
-    return base + (0.5 + q.astype(np.float64) / 65536.0) * pitch, hq * pitch
+    plane = lambda q: base + (0.5 + q.astype(np.float64) / 65536.0) * pitch
+    return plane(qmin), plane(qmax)
 
 
 def walk_pairs(sc_bvh, nodes, info):
@@ -66,7 +75,7 @@ def test_quantised_boxes_enclose_the_exact_ones(name):
         assert info["n_inner"] == 0
         return
     assert info["n_inner"] == n_tris - 1
-    c, h = decode(nodes, info)
+    pmin, pmax = decode(nodes, info)
     pairs = walk_pairs(sc["BVH"], nodes, info)
     assert len(pairs) == info["n_inner"]
     rec = np.array([p[0] for p in pairs])
@@ -75,16 +84,77 @@ def test_quantised_boxes_enclose_the_exact_ones(name):
     for side in (0, 1):
         ch = bvh[node, side].astype(int)
         mn, mx = bvh[ch, 2:5], bvh[ch, 5:8]
-        lo, hi = c[rec, side] - h[rec, side], c[rec, side] + h[rec, side]
+        lo, hi = pmin[rec, side], pmax[rec, side]
         tol = 1e-12 * (np.abs(mn) + np.abs(mx) + 1.0)          # binary64 evaluation of the test itself
         assert (lo <= mn + tol).all() and (hi >= mx - tol).all()
-        worst = max(worst, float(((hi - lo) - (mx - mn)).max() / info["grid_pitch"].max()))
-    assert worst < 2.0 ** -6                                    # never looser than bf16 rounding of a scene-sized box
+        worst = max(worst, float((((hi - lo) - (mx - mn)) / info["grid_pitch"]).max()))
+    assert worst < 5.0 / 65536.0                                # never looser than a few grid cells
     # the root box in record units encloses node 0
-    rc = info["grid_base"].astype(np.float64) + info["root_fc"].astype(np.float64) * info["grid_pitch"]
-    rh = info["root_hq"].astype(np.float64) * info["grid_pitch"]
-    assert (rc - rh <= bvh[0, 2:5] + 1e-12).all() and (rc + rh >= bvh[0, 5:8] - 1e-12).all()
+    base, pitch = info["grid_base"].astype(np.float64), info["grid_pitch"].astype(np.float64)
+    rlo = base + (0.5 + info["root_qmin"].astype(np.float64) / 65536.0) * pitch
+    rhi = base + (0.5 + info["root_qmax"].astype(np.float64) / 65536.0) * pitch
+    assert (rlo <= bvh[0, 2:5]).all() and (rhi >= bvh[0, 5:8]).all()
+    ext = bvh[0, 5:8] - bvh[0, 2:5]
+    assert ((rhi - rlo) <= np.maximum(ext, ext.max() / 256.0) * 1.001 + 4 * pitch / 65536.0).all()   # and not much more
     assert info["cmax"] >= np.abs(bvh[:, 2:8]).max()
+
+
+@pytest.mark.parametrize("name", ["cornell", "monkey", "furnace", "serre", "proto", "height_field"])
+def test_own_culling_tree_holds_every_triangle_once_inside_enclosing_boxes(name):
+    """csrc/cull_tree.cpp: a different topology over the SAME leaf boxes.  Every triangle must hang under exactly one
+    leaf ref, every child box must enclose the leaf boxes of BVH.py's array beneath it, and the reported depth must
+    bound the levels (it sizes the traversal stacks)."""
+    if name == "height_field":
+        import ensem3a_openclraytracer_b200 as rt
+        from tests.synthetic import height_field_scene
+        sc = height_field_scene(64, seed=3)
+        sc["BVH"] = rt.build_bvh(sc["faceData"], sc["V_p"])
+    else:
+        sc = fixtures.load_scene(name)
+    nodes, info = probe(sc, own_tree=True)
+    assert info["canonical"] and info["fast_ok"]
+    bvh = sc["BVH"].reshape(-1, 9).astype(np.float64)
+    n_tris = sc["faceData"].size // 10
+    assert info["n_inner"] == n_tris - 1
+    leaf = bvh[bvh[:, 8] != -1]
+    tmin = np.zeros((n_tris, 3)); tmax = np.zeros((n_tris, 3))
+    tmin[leaf[:, 8].astype(int)] = leaf[:, 2:5]
+    tmax[leaf[:, 8].astype(int)] = leaf[:, 5:8]
+    pmin, pmax = decode(nodes, info)
+    nf4 = info["node_f4"]
+    refs = nodes[:, 6:8].astype(np.int64)
+    refs = np.where(refs >= 1 << 31, refs - (1 << 32), refs)
+    seen = np.zeros(n_tris, int)
+    # post-order: exact box of every sub-tree = union of the leaf boxes beneath
+    sub = {}
+    deepest = 0
+    stack = [(0, 0, False)]
+    while stack:
+        rec, level, done = stack.pop()
+        if not done:
+            stack.append((rec, level, True))
+            for side in (0, 1):
+                r = int(refs[rec, side])
+                if r >= 0:
+                    assert r % nf4 == 0 and 0 < r // nf4 < info["n_inner"]
+                    stack.append((r // nf4, level + 1, False))
+            continue
+        lo = np.full(3, np.inf); hi = np.full(3, -np.inf)
+        for side in (0, 1):
+            r = int(refs[rec, side])
+            if r < 0:
+                t = ~r
+                seen[t] += 1
+                clo, chi = tmin[t], tmax[t]
+                deepest = max(deepest, level + 1)
+            else:
+                clo, chi = sub.pop(r // nf4)
+            assert (pmin[rec, side] <= clo).all() and (pmax[rec, side] >= chi).all()
+            assert ((pmax[rec, side] - pmin[rec, side]) - (chi - clo) <= 5.0 / 65536.0 * info["grid_pitch"]).all()
+            lo = np.minimum(lo, clo); hi = np.maximum(hi, chi)
+        sub[rec] = (lo, hi)
+    assert (seen == 1).all()
+    assert deepest == info["cull_depth"]
 
 
 def renumber(bvh9):
