@@ -58,7 +58,7 @@ struct b200rt_ctx {
   float cull_abs = 0.0f, cmax = 0.0f;
   int fast_ok = 1;
   // k_trace tuning knobs (B200RT_QUORUM / B200RT_REFILL_MIN / B200RT_TRI_QUORUM / B200RT_STEPS override)
-  int quorum = 20, refill_min = 8, tri_quorum = 4;
+  int quorum = 12, refill_min = 8, tri_quorum = 2;
   int carveout = -1;       // B200RT_CARVEOUT: k_trace's shared-memory carve-out (-1 driver's choice, 0 computed, else per cent)
   int max_trace_ctas = 0;  // B200RT_MAX_TRACE_CTAS: cap on resident k_trace CTAs per SM (0 = what fits)
   int compact_every = 8;   // B200RT_COMPACT_EVERY: wavefront iterations between two compactions of the path list

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "scene_repack.h"
@@ -21,7 +22,7 @@ namespace b200rt {
 
 namespace {
 
-constexpr int kBins = 16;
+constexpr int kBins = 64;             // capacity; the number in use is Builder::bins
 constexpr int kSahLevels = 64;        // below this level ranges are halved by index: bounds the depth at 64 + log2(n)
 constexpr int kTaskMin = 2048;        // sub-trees smaller than this are built by the task that reached them
 constexpr int kParallelBin = 1 << 18; // ranges larger than this are binned by several tasks
@@ -69,9 +70,10 @@ struct Builder {
   const float *hi(int t) const { return &tb[2 * (size_t)t + 1].x; }
   float centre(int t, int a) const { return 0.5f * lo(t)[a] + 0.5f * hi(t)[a]; }
 
-  static int bin_of(float c, float c0, float scale) {
+  int bins = 32;
+  int bin_of(float c, float c0, float scale) const {
     int b = (int)((c - c0) * scale);
-    return b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+    return b < 0 ? 0 : (b >= bins ? bins - 1 : b);
   }
 
   void bin_range(int begin, int end, const float *c0, const float *scale, Bins *out) const {
@@ -106,7 +108,7 @@ struct Builder {
       bool any = false;
       for (int a = 0; a < 3; ++a) {
         const float e = c1[a] - c0[a];
-        scale[a] = (e > 0.0f && std::isfinite(e)) ? (float)kBins * (1.0f - 0x1p-20f) / e : 0.0f;
+        scale[a] = (e > 0.0f && std::isfinite(e)) ? (float)bins * (1.0f - 0x1p-20f) / e : 0.0f;
         if (!std::isfinite(scale[a])) scale[a] = 0.0f;
         any = any || scale[a] > 0.0f;
       }
@@ -136,7 +138,7 @@ struct Builder {
           Box acc;
           acc.reset();
           int c = 0;
-          for (int b = kBins - 1; b > 0; --b) {
+          for (int b = bins - 1; b > 0; --b) {
             if (B.cnt[a][b]) acc.grow(B.box[a][b]);
             c += B.cnt[a][b];
             right_area[b] = c ? acc.half_area() : 0.0;
@@ -144,7 +146,7 @@ struct Builder {
           }
           acc.reset();
           c = 0;
-          for (int b = 0; b < kBins - 1; ++b) {   // split after bin b
+          for (int b = 0; b < bins - 1; ++b) {   // split after bin b
             if (B.cnt[a][b]) acc.grow(B.box[a][b]);
             c += B.cnt[a][b];
             if (c == 0 || right_cnt[b + 1] == 0) continue;
@@ -219,6 +221,10 @@ void build_cull_tree(const Repacked::f4 *tboxes, int n_tris, std::vector<CullNod
   B.tb = tboxes;
   B.idx = idx.data();
   B.nodes = tmp.data();
+  if (const char *q = getenv("B200RT_CULL_BINS")) {   // development knob
+    const int v = atoi(q);
+    if (v >= 2 && v <= kBins) B.bins = v;
+  }
   Box root;
 #pragma omp parallel
 #pragma omp single

@@ -338,12 +338,13 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     float hk = 0.0f, pb_ray = 0.0f;
     int htri = -1;
     if (valid) {
-      const float4 sb = A.pB[pix];
+      // all four at once: they depend on pix only (on a path's first iteration pA / pC / pHit hold nothing yet and
+      // are not looked at), and this kernel is bound by the latency of its chains of dependent loads
+      const float4 sb = A.pB[pix], sa = A.pA[pix], sc = A.pC[pix];
+      const int2 hh = A.pHit[pix];
       meta = __float_as_uint(sb.z);
       g.a = __float_as_uint(sb.w);
       if (!(meta & 1u)) {
-        const float4 sa = A.pA[pix], sc = A.pC[pix];
-        const int2 hh = A.pHit[pix];
         o = mk3(sa.x, sa.y, sa.z);
         d = mk3(sa.w, sb.x, sb.y);
         acc = mk3(sc.x, sc.y, sc.z);

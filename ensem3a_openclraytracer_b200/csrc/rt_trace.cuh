@@ -150,10 +150,10 @@ RT_DEV bool slab_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, f
 // Error budget per axis, in units of u (cmax + |o|) |r| with u = 2^-24.  b200rt_set_scene makes cmax bound every
 // |box plane|, |vertex coordinate|, |base| and |base + pitch|, hence pitch <= 2 cmax and |x| <= cmax for every decoded
 // plane.  A = RN(pitch·r), scaled by fq < 1: 2.  B: one rounding of base - o (<= cmax + |o|) and one of the product: 2.
-// Bn / Bf: 1.  r against 1/d: 1.  The FMA: 2 (|result| <= (2 cmax + |o|)|r| + m).  Together 8.  The reference's own
+// Bn / Bf: 1.  r (the hardware's approximate reciprocal, within 1 ulp) against 1/d: 2.  The FMA: 2 (|result| <= (2 cmax + |o|)|r| + m).  Together 9.  The reference's own
 // t = RN(RN(p - o) / d) is within 2 of the real (p - o)/d.  The margin, PER AXIS (a ray with one tiny direction
 // component must not lose the culling of the other two axes),
-//     m = 2^-18 (cmax + |o|) |r|        (= 64 units, six times the sum of 10),
+//     m = 2^-18 (cmax + |o|) |r|        (= 64 units, six times the sum of 11),
 // gives  lo <= tmin_exact  and  hi >= tmax_exact: the box certainly fails the reference's test when hi < lo.
 // Valid while every |d| component lies in [2^-40, 2^40] and |o|, cmax <= 2^40 (no overflow, no denormal r).
 struct RayFast {
@@ -193,7 +193,9 @@ RT_DEV void rayfast_axis(float o, float d, float cmax, float cull_abs, float bas
   *sf = neg ? kSelMin : kSelMax;
   float rr, extra = 0.0f;
   if (a >= 9.094947017729282e-13f /* 2^-40 */ && a <= 1.099511627776e12f /* 2^40 */) {
-    rr = __frcp_rn(d);
+    // the hardware approximation (within 1 ulp of 1/d: 2 units of the budget above instead of 1; no denormal in or out
+    // for |d| in [2^-40, 2^40]) — these intervals only cull, and the correctly rounded reciprocal costs four times as much
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(d));
   } else if (a < 9.094947017729282e-13f) {
     rr = copysignf(1.099511627776e12f, d);
     extra = 1002.0f + 2.0f * cull_abs;
