@@ -332,6 +332,15 @@ def main():
     ctx.render_device(cam, env, W, H, spp, mb, out_dev.data_ptr(), o)
     st = ctx.stats()
     box_per_ray, tri_per_ray = st["box_tests"] / st["rays"], st["tri_tests"] / st["rays"]
+    # the same rays in the reference's own walk (BVH.py's tree, right-first, no culling: MathLib.cl:234-288) — SURVEY 8d's
+    # per-ray figure; the 5 M-triangle scene is skipped (seconds per sample in that order)
+    ref_box_per_ray = ref_tri_per_ray = None
+    if args.config != "5":
+        o = rt.make_opts(traversal=rt.TRAVERSAL_REFERENCE, stack_cap=64, collect_stats=True, output=rt.OUT_SUMS, sample_begin=0,
+                         sample_end=1, **philox1)
+        ctx.render_device(cam, env, W, H, spp, mb, out_dev.data_ptr(), o)
+        st = ctx.stats()
+        ref_box_per_ray, ref_tri_per_ray = st["box_tests"] / st["rays"], st["tri_tests"] / st["rays"]
 
     # ---- device-resident timing ------------------------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -467,7 +476,18 @@ def main():
                     "frac_of_whole_step": (rays_step - npix) / world * instr_per_ray / (ms_per_step * 1e-3) / 1e9 / peak,
                     "l2_bytes_per_ray_this_layout": bytes_per_ray,
                     "note": "scene is cache-resident (SURVEY 8d): the bound is the SM issue rate; algorithmic work = 40 "
-                            "thread-instructions per box test + 80 per triangle test of the production (FAST) traversal"}
+                            "thread-instructions per box test + 80 per triangle test, counted on the production (FAST) "
+                            "traversal of the production culling tree — work actually done, so frac falls when a better "
+                            "tree removes work faster than it removes time (reference_work has SURVEY 8d's own figure)"}
+        if ref_box_per_ray is not None:
+            ref_instr = INSTR_PER_BOX * ref_box_per_ray + INSTR_PER_TRI * ref_tri_per_ray
+            ref_achieved = trace_rays * ref_instr / trace_s / 1e9
+            roofline["reference_work"] = {
+                "box_tests_per_ray": ref_box_per_ray, "tri_tests_per_ray": ref_tri_per_ray, "thread_instr_per_ray": ref_instr,
+                "achieved": ref_achieved, "frac": ref_achieved / peak,
+                "note": "SURVEY 8d's per-ray figure: box / triangle tests the reference's own walk (right-first over BVH.py's "
+                        "tree, no culling) spends on the same rays, counted on the GPU in reference order over 1 spp; "
+                        "divided by the same k_trace time.  Work the task needs done, not work this kernel performs"}
     roofline.update(common)
 
     line = {

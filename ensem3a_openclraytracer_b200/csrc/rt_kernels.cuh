@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     const unsigned int t = tb + lane;
     const bool in_part = t < part_end;
     // ---- phase 0: load -------------------------------------------------------------------------------------------
-    int pix = in_part ? list_in[t] : -1;
+    int pix = in_part ? ld_stream(list_in + t) : -1;
     const bool valid = pix >= 0;   // -1: past the part's end, or a path that left the wavefront since the last compaction
     if (!valid) pix = 0;
     uint32_t meta = 1u;
@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     if (valid) {
       // all four at once: they depend on pix only (on a path's first iteration pA / pC / pHit hold nothing yet and
       // are not looked at), and this kernel is bound by the latency of its chains of dependent loads
-      const float4 sb = A.pB[pix], sa = A.pA[pix], sc = A.pC[pix];
-      const int2 hh = A.pHit[pix];
+      const float4 sb = ld_stream(A.pB + pix), sa = ld_stream(A.pA + pix), sc = ld_stream(A.pC + pix);
+      const int2 hh = ld_stream(A.pHit + pix);
       meta = __float_as_uint(sb.z);
       g.a = __float_as_uint(sb.w);
       if (!(meta & 1u)) {
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     }
     if (end_sample) {
       float *acc_px = A.out + 3 * (size_t)pix;
-      v3 sum = mk3(acc_px[0], acc_px[1], acc_px[2]);
+      v3 sum = mk3(ld_stream(acc_px), ld_stream(acc_px + 1), ld_stream(acc_px + 2));
       if (NEE) {
         const float4 r = A.pR[pix];
         acc = mk3(r.x, r.y, r.z) + acc;   // direct light gathered along the path + what the path ended on
@@ -462,11 +462,11 @@ __global__ void __launch_bounds__(kShadeBlock, 8) k_shade(const __grid_constant_
     }
     // ---- phase 3: a new sample starts from the cached primary hit (Raytracing.cl:195-201) --------------------------------------
     if (start) {
-      const float4 dk = A.prim_dirk[pix];
+      const float4 dk = ld_stream(A.prim_dirk + pix);
       o = F.cam_pos;
       d = mk3(dk.x, dk.y, dk.z);
       hk = dk.w;
-      htri = A.prim_tri[pix];
+      htri = ld_stream(A.prim_tri + pix);
       acc = mk3(1.0f, 1.0f, 1.0f);
       j = 0;
       if (NEE) {
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
   unsigned int c_next = 0, c_end = 0;  // the warp's claimed chunk of the list (uniform)
   bool exhausted = false;
 
-  unsigned long long rays = 0;
+  unsigned int rays = 0;   // of this lane: far below 2^32
   unsigned int mism = 0;
   TraceCounters tc;
   tc.box_tests = 0; tc.tri_tests = 0;
@@ -669,9 +669,9 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
         const int take = min(need, (int)(c_end - c_next));
         if (want && rank < take) {
           want = false;
-          path = list[c_next + rank];
+          path = ld_stream(list + c_next + rank);
           if (path >= 0) {   // -1: the path left the wavefront since the last compaction; the lane waits for the next refill
-            const float4 sa = A.pA[path], sb = A.pB[path];
+            const float4 sa = ld_stream(A.pA + path), sb = ld_stream(A.pB + path);
             const v3 o = mk3(sa.x, sa.y, sa.z);
             const v3 d = ((__float_as_uint(sb.z) >> 3) & 1u) ? A.F.sun_dir : mk3(sa.w, sb.x, sb.y);
             rays++;
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ Kernel
     }
   }
   if (lane == 0) {
-    atomicAdd(&A.counters->rays, rays);
+    atomicAdd(&A.counters->rays, (unsigned long long)rays);
     if (mism) atomicAdd(&A.counters->mismatches, (unsigned long long)mism);
     if (STATS) {
       atomicAdd(&A.counters->box_tests, tc.box_tests);

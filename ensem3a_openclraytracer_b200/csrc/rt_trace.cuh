@@ -90,6 +90,36 @@ struct Hit {
   float k;    // 1000 on a miss, like H.k (MathLib.cl:239)
 };
 
+// Path state is read once per kernel and streams through the SM: these loads do not allocate a line in L1, which is
+// left to the nodes and triangles the lanes come back to.
+#ifdef B200RT_NO_STREAM   // development A/B
+RT_DEV float4 ld_stream(const float4 *p) { return *p; }
+RT_DEV int2 ld_stream(const int2 *p) { return *p; }
+RT_DEV int ld_stream(const int *p) { return *p; }
+RT_DEV float ld_stream(const float *p) { return *p; }
+#else
+RT_DEV float4 ld_stream(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+RT_DEV int2 ld_stream(const int2 *p) {
+  int2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+RT_DEV int ld_stream(const int *p) {
+  int v;
+  asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+RT_DEV float ld_stream(const float *p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+#endif
+
 template <bool SMEM>
 RT_DEV float4 ld4(const float4 *p) {
   if (SMEM) return *p;
@@ -396,7 +426,10 @@ RT_DEV float cull_limit(const SceneView &S, const Trav &T) { return __fmaf_rn(T.
 // Leaves whose box passes the conservative test are not tested on the spot (only a few lanes of a warp reach a
 // leaf in the same turn) but parked, at most kParkCap per lane (entry e of lane l at parks[e * stride]); the
 // warp tests parked triangles together.  Last in, first out; of a pair of leaves the farther is parked first.
-constexpr int kParkCap = 4;
+#ifndef B200RT_PARK_CAP
+#define B200RT_PARK_CAP 6
+#endif
+constexpr int kParkCap = B200RT_PARK_CAP;
 
 // starts a traversal of a ray for which ray_is_fast() holds
 template <bool SMEM, bool STATS>
