@@ -429,9 +429,25 @@ int read_counters_one(b200rt_ctx *c) {
   if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]) == cudaSuccess) c->stats.total_ms = ms;
   c->stats.shade_kernel_ms = 0.0f;
   c->stats.trace_kernel_ms = 0.0f;
+  // B200RT_DUMP_WAVE=<file> (development): one line per wavefront iteration — live paths, k_shade ms, k_trace ms
+  FILE *dump = nullptr;
+  std::vector<unsigned int> live;
+  if (c->kev_used > 1)
+    if (const char *path = getenv("B200RT_DUMP_WAVE")) {
+      dump = fopen(path, "w");
+      live.resize((size_t)c->kev_used / 2 + 2, 0u);
+      if (cudaMemcpy(live.data(), c->d_cnt.p, live.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost) != cudaSuccess) live.assign(live.size(), 0u);
+    }
+  float shade_ms = 0.0f;
   for (int i = 0; i + 1 < c->kev_used; ++i)  // event i sits before launch i; launches alternate shade, trace, shade, ...
-    if (cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]) == cudaSuccess)
+    if (cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]) == cudaSuccess) {
       ((i & 1) ? c->stats.trace_kernel_ms : c->stats.shade_kernel_ms) += ms;
+      if (dump) {
+        if (i & 1) fprintf(dump, "%d %u %.4f %.4f\n", i / 2, live[(size_t)i / 2], shade_ms, ms);
+        else shade_ms = ms;
+      }
+    }
+  if (dump) fclose(dump);
   c->kev_used = 0;
   c->stats_pending = false;
   return 0;
