@@ -241,10 +241,13 @@ int b200rt_multi_get_stats(const b200rt_multi *m, b200rt_stats *stats);
 
 /* Host-only view of what b200rt_set_scene uploads (no context, no GPU): validates the buffers exactly as
  * b200rt_set_scene does and writes the repacked interior-node records (8 x uint32 each, csrc/rt_trace.cuh "repacked
- * scene") to nodes_out (capacity in uint32 words; may be NULL to query).  info_out (24 floats): [0] interior nodes,
- * [1] 16-byte units per node, [2] tree depth, [3] stack entries the reference-order walk needs, [4] canonical (fast
- * traversal applies), [5] fast_ok, [6] cmax, [7] cull_abs, [8..10] grid base, [11..13] grid pitch, [14..16] root fc,
- * [17..19] root hq, [20..22] host milliseconds of the three stages (triangles, tree walk, node records).  rank_out (one
+ * scene") to nodes_out (capacity in uint32 words; may be NULL to query).  The records hold the culling tree built over
+ * the caller's leaf boxes (csrc/cull_tree.cpp), or the caller's own topology when B200RT_CULL_TREE=0 is set in the
+ * environment.  info_out (24 floats): [0] interior nodes, [1] 16-byte units per node, [2] depth of the caller's tree,
+ * [3] stack entries the reference-order walk needs, [4] canonical (fast traversal applies), [5] fast_ok, [6] cmax,
+ * [7] cull_abs, [8..10] grid base, [11..13] grid pitch, [14..16] grid index of the root box's min planes, [17..19] of its
+ * max planes, [20..22] host milliseconds of the three stages (triangles, tree walk, node records incl. the culling
+ * tree), [23] depth of the tree in the records (level of its deepest leaf; sizes the traversal stacks).  rank_out (one
  * int32 per triangle, may be NULL): the triangle's position in the reference's visiting order, which breaks distance
  * ties.  Lets the CPU test-suite check that every quantised box encloses the exact one. */
 int b200rt_repack_probe(const float *vertex_p, int64_t n_vertex_p, const float *vertex_n, int64_t n_vertex_n,
