@@ -63,7 +63,7 @@ struct b200rt_ctx {
   int max_trace_ctas = 0;  // B200RT_MAX_TRACE_CTAS: cap on resident k_trace CTAs per SM (0 = what fits)
   int stream_trace_ctas = 4;  // B200RT_STREAM_TRACE_CTAS: the cap while three or more sample streams share the GPU (0 = none)
   int frame_trace_cap = 0; // the cap of the frame being enqueued (set by render_frame)
-  int compact_every = 8;   // B200RT_COMPACT_EVERY: wavefront iterations between two compactions of the path list
+  int compact_every = 4;   // B200RT_COMPACT_EVERY: wavefront iterations between two compactions of the path list
   std::vector<int32_t> tri_mat;  // for re-validating material edits
   DevBuf d_light;                // triangles whose material is emissive, ascending (opt-in light sampling)
   int n_light = 0;

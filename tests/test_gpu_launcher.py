@@ -232,9 +232,9 @@ def test_per_kernel_timing_stats(gpu_ctx):
     cam, env = fixtures.cam_env(sc["params"], 128)
     a = gpu_ctx.render(cam, env, 128, 128, 4, 4, opts=rt.make_opts(time_kernels=True))
     st = gpu_ctx.stats()
-    # k_primary + the first list's (k_count_parts, k_compact) + n_iter x (k_shade, k_trace) + a compaction every 8th
+    # k_primary + the first list's (k_count_parts, k_compact) + n_iter x (k_shade, k_trace) + a compaction every 4th
     # iteration + closing k_shade
-    assert st["kernel_launches"] == 1 + 2 + 2 * 4 * 6 + (4 * 6) // 8 + 1
+    assert st["kernel_launches"] == 1 + 2 + 2 * 4 * 6 + (4 * 6) // 4 + 1
     assert st["wave_iterations"] == 4 * 6
     assert st["trace_kernel_ms"] > 0 and st["shade_kernel_ms"] > 0
     assert st["trace_kernel_ms"] + st["shade_kernel_ms"] <= st["total_ms"] * 1.05
