@@ -46,7 +46,7 @@ struct b200rt_ctx {
   bool have_scene = false;
   bool have_scene_cached = false;  // scene_hash / ibl_hash are valid
   uint64_t scene_hash = 0, mat_hash = 0;
-  DevBuf d_nodes, d_tris, d_normals, d_tboxes, d_frames, d_mats, d_bvh9, d_leafcnt;
+  DevBuf d_nodes, d_tris, d_ctris, d_normals, d_tboxes, d_frames, d_mats, d_bvh9, d_leafcnt;
   int n_nodes9 = 0, n_inner = 0, n_tris = 0, n_mats = 0;
   int depth = 0, ref_stack_need = 0;
   int cull_depth = 0;      // depth of the tree the node records hold (the culling tree, scene_repack.h)
@@ -224,6 +224,7 @@ void fill_args(b200rt_ctx *c, const FrameParams &F, const b200rt_opts &o, float 
   S.nodes = static_cast<const uint4 *>(c->d_nodes.p);
   S.node_f4 = c->node_f4;
   S.tris = static_cast<const float4 *>(c->d_tris.p);
+  S.ctris = static_cast<const float4 *>(c->d_ctris.p);
   S.normals = static_cast<const float4 *>(c->d_normals.p);
   S.tboxes = static_cast<const float4 *>(c->d_tboxes.p);
   S.frames = static_cast<const float4 *>(c->d_frames.p);
@@ -630,7 +631,7 @@ int render_impl(b200rt_ctx *c, const float *cam, const float *env, int width, in
 // part's tracing (the two kernels are bound by different units).
 void borrow_scene(b200rt_ctx *p, b200rt_ctx *h) {
   auto lend = [](DevBuf &dst, const DevBuf &src) { dst.p = src.p; dst.cap = src.cap; dst.borrowed = true; };
-  lend(h->d_nodes, p->d_nodes); lend(h->d_tris, p->d_tris); lend(h->d_normals, p->d_normals); lend(h->d_tboxes, p->d_tboxes);
+  lend(h->d_nodes, p->d_nodes); lend(h->d_tris, p->d_tris); lend(h->d_ctris, p->d_ctris); lend(h->d_normals, p->d_normals); lend(h->d_tboxes, p->d_tboxes);
   lend(h->d_frames, p->d_frames); lend(h->d_mats, p->d_mats); lend(h->d_bvh9, p->d_bvh9); lend(h->d_leafcnt, p->d_leafcnt);
   lend(h->d_light, p->d_light);
   h->n_light = p->n_light;
@@ -837,7 +838,7 @@ void b200rt_destroy(b200rt_ctx *c) {
     c->ibl_tex = 0;
     c->ibl_array = nullptr;
   }
-  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_normals, &c->d_tboxes, &c->d_frames, &c->d_mats, &c->d_bvh9, &c->d_leafcnt, &c->d_prim_dirk,
+  DevBuf *bufs[] = {&c->d_nodes, &c->d_tris, &c->d_ctris, &c->d_normals, &c->d_tboxes, &c->d_frames, &c->d_mats, &c->d_bvh9, &c->d_leafcnt, &c->d_prim_dirk,
                     &c->d_prim_tri, &c->d_out, &c->d_misc, &c->d_tmp_a, &c->d_tmp_b, &c->d_pA, &c->d_pB, &c->d_pC,
                     &c->d_pHit, &c->d_list0, &c->d_list1, &c->d_cnt, &c->d_slots, &c->d_part_count, &c->d_light, &c->d_pS,
                     &c->d_pL, &c->d_pR};
@@ -935,6 +936,7 @@ int upload_scene(b200rt_ctx *c, const Repacked &R, const SceneArgs &a, uint64_t 
   const int n_tris = R.n_tris;
   CU(cudaSetDevice(c->device));
   if (ensure(c, c->d_tris, R.tris.size() * sizeof(float4))) return B200RT_ERR_CUDA;
+  if (ensure(c, c->d_ctris, R.ctris.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_normals, R.normals.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_tboxes, R.tboxes.size() * sizeof(float4))) return B200RT_ERR_CUDA;
   if (ensure(c, c->d_frames, (size_t)n_tris * kFrameVec * sizeof(float4))) return B200RT_ERR_CUDA;
@@ -943,6 +945,7 @@ int upload_scene(b200rt_ctx *c, const Repacked &R, const SceneArgs &a, uint64_t 
   if (ensure(c, c->d_leafcnt, R.leaf_count.size() * sizeof(int32_t))) return B200RT_ERR_CUDA;
   CU(cudaMemcpyAsync(c->d_leafcnt.p, R.leaf_count.data(), R.leaf_count.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_tris.p, R.tris.data(), R.tris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_ctris.p, R.ctris.data(), R.ctris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_normals.p, R.normals.data(), R.normals.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_tboxes.p, R.tboxes.data(), R.tboxes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   if (!R.nodes.empty())

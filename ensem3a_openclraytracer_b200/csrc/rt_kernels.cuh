@@ -99,7 +99,7 @@ RT_DEV SceneView stage_scene(const KernelArgs &A, unsigned char *smem, size_t *u
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(nb + tb)
                  : "memory");
     if (nb) bulk_g2s(s_nodes, A.S.nodes, nb, &bar);
-    bulk_g2s(s_tris, A.S.tris, tb, &bar);
+    bulk_g2s(s_tris, A.S.ctris, tb, &bar);
     uint32_t done = 0;  // one thread waits for the bytes to land; the block barrier publishes them
     while (!done) {
       asm volatile(
@@ -113,7 +113,7 @@ RT_DEV SceneView stage_scene(const KernelArgs &A, unsigned char *smem, size_t *u
   }
   __syncthreads();
   S.nodes = s_nodes;
-  S.tris = s_tris;
+  S.ctris = s_tris;
   *used = (size_t)nb + tb;
   return S;
 }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Kern
         int mat_type = -1;
         float emit = 0.0f;
         if (h.tri >= 0) {
-          int mat = __float_as_int(ld4<SMEM>(S.tris + 3 * (size_t)h.tri + 2).y);
+          int mat = __float_as_int(__ldg(S.tris + 3 * (size_t)h.tri + 2).y);
           Material m = load_material(S.mats, mat);
           mat_type = m.type;
           emit = m.roughness;

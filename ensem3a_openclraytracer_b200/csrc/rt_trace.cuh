@@ -61,7 +61,9 @@ namespace b200rt {
 struct SceneView {
   const uint4 *nodes;
   int node_f4;              // 16-byte units per node: 2, or 3 for a scene small enough to be staged in shared memory
-  const float4 *tris;
+  const float4 *tris;       // by triangle id
+  const float4 *ctris;      // the same records in the order of the culling tree's leaves: what leaf refs index and the
+                            // traversal tests (staged in shared memory for small scenes); t2.w = triangle id
   const float4 *normals;
   const float4 *tboxes;
   const float4 *frames;     // kFrameVec float4 per triangle (rt_shade.cuh)
@@ -289,15 +291,15 @@ RT_DEV bool tri_hit(v3 o, v3 d, v3 A, v3 e1, v3 e2, float *k_out) {
 }
 
 template <bool SMEM>
-RT_DEV void test_triangle(const SceneView &S, int t, v3 o, v3 d, Hit &best, int &best_rank) {
-  const float4 *p = S.tris + 3 * (size_t)t;
+RT_DEV void test_triangle(const SceneView &S, int leaf, v3 o, v3 d, Hit &best, int &best_rank) {
+  const float4 *p = S.ctris + 3 * (size_t)leaf;
   float4 t0 = ld4<SMEM>(p), t1 = ld4<SMEM>(p + 1), t2 = ld4<SMEM>(p + 2);
   float k;
   if (tri_hit(o, d, mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), &k) && k > 0.0001f) {
     int rank = __float_as_int(t2.z);
     if (k < best.k || (k == best.k && best.tri >= 0 && rank < best_rank)) {
       best.k = k;
-      best.tri = t;
+      best.tri = __float_as_int(t2.w);
       best_rank = rank;
     }
   }
@@ -364,7 +366,7 @@ RT_DEV Hit closest_hit_reference_cap(const SceneView &S, v3 o, v3 d, TraceCounte
     if (t != -1) {
       if (STATS) cnt->tri_tests++;
       const float4 *p = S.tris + 3 * (size_t)t;
-      float4 t0 = ld4<SMEM>(p), t1 = ld4<SMEM>(p + 1), t2 = ld4<SMEM>(p + 2);
+      float4 t0 = __ldg(p), t1 = __ldg(p + 1), t2 = __ldg(p + 2);
       float k;
       if (tri_hit(o, d, mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), &k) && k < best.k &&
           k > 0.0001f) {

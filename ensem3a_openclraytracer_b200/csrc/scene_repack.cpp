@@ -407,6 +407,17 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
         }
       }
       }
+      // Leaf refs index `ctris`: the triangle records once more, in the order the leaves appear in the node records, so
+      // that the leaves of a sub-tree — the triangles neighbouring rays test — share cache lines whatever the order of
+      // the caller's face list.
+      std::vector<int> leaf_pos;
+      if (R.cull_tree) {
+        leaf_pos.assign((size_t)n_tris, -1);
+        int pos = 0;
+        for (size_t q = 0; q < cull.size(); ++q)
+          for (int k = 0; k < 2; ++k)
+            if (cull[q].ref[k] < 0) leaf_pos[(size_t)~cull[q].ref[k]] = pos++;
+      }
       const int n_inner = R.cull_tree ? (int)cull.size() : (int)order.size();
       R.n_inner = n_inner;
       // small scenes are staged in shared memory with 48-byte node spacing (SceneView::node_f4)
@@ -421,8 +432,8 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
         if (R.cull_tree) {
           const CullNode &N = cull[q];
           bl = N.box[0]; br = N.box[1];
-          refl = N.ref[0] < 0 ? N.ref[0] : N.ref[0] * nf4;
-          refr = N.ref[1] < 0 ? N.ref[1] : N.ref[1] * nf4;
+          refl = N.ref[0] < 0 ? ~leaf_pos[(size_t)~N.ref[0]] : N.ref[0] * nf4;
+          refr = N.ref[1] < 0 ? ~leaf_pos[(size_t)~N.ref[1]] : N.ref[1] * nf4;
         } else {
           const int cur = order[q];
           const int l = L(cur), r = Rc(cur);
@@ -442,12 +453,35 @@ int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, c
         R.nodes[(size_t)nf4 * q + 1] = b;
         if (nf4 == 3) R.nodes[(size_t)nf4 * q + 2] = Repacked::u4{0, 0, 0, 0};
       }
+      if (R.cull_tree) {
+        R.ctris.resize((size_t)n_tris * 3);
+#pragma omp parallel for schedule(static)
+        for (int t = 0; t < n_tris; ++t) {
+          const size_t p = (size_t)leaf_pos[(size_t)t];
+          R.ctris[3 * p] = R.tris[3 * (size_t)t];
+          R.ctris[3 * p + 1] = R.tris[3 * (size_t)t + 1];
+          Repacked::f4 t2 = R.tris[3 * (size_t)t + 2];
+          t2.w = as_float((uint32_t)t);
+          R.ctris[3 * p + 2] = t2;
+        }
+      }
       if (outside) {   // cannot happen for nested boxes; such a tree is walked in reference order
         R.canonical = false;
         R.nodes.clear();
         R.n_inner = 0;
         R.node_f4 = 2;
       }
+    }
+  }
+  if (R.ctris.size() != R.tris.size() || !R.cull_tree || !R.canonical) {   // leaf refs are triangle ids
+    R.ctris.resize(R.tris.size());
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < n_tris; ++t) {
+      R.ctris[3 * (size_t)t] = R.tris[3 * (size_t)t];
+      R.ctris[3 * (size_t)t + 1] = R.tris[3 * (size_t)t + 1];
+      Repacked::f4 t2 = R.tris[3 * (size_t)t + 2];
+      t2.w = as_float((uint32_t)t);
+      R.ctris[3 * (size_t)t + 2] = t2;
     }
   }
   R.ms_nodes = now_ms() - t2;
@@ -482,6 +516,12 @@ extern "C" int b200rt_repack_probe(const float *vp, int64_t n_vp, const float *v
       const b200rt::Repacked::u4 &a = R.nodes[(size_t)R.node_f4 * q], &b = R.nodes[(size_t)R.node_f4 * q + 1];
       uint32_t *o = nodes_out + 8 * (size_t)q;
       o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+      for (int k = 6; k < 8; ++k)   // leaf refs index `ctris`: reported as the triangle they stand for
+        if ((int32_t)o[k] < 0) {
+          uint32_t id;
+          memcpy(&id, &R.ctris[3 * (size_t)~(int32_t)o[k] + 2].w, 4);
+          o[k] = (uint32_t)~(int32_t)id;
+        }
     }
   }
   return 0;

@@ -27,6 +27,8 @@ struct Repacked {
   struct u4 { uint32_t x, y, z, w; };
   raw_vector<u4> nodes;         // node_f4 x 16 bytes per interior node (rt_trace.cuh "repacked scene")
   raw_vector<f4> tris, normals, tboxes;
+  raw_vector<f4> ctris;         // the triangle records in the order of the culling tree's leaves (what leaf refs index); .w of the
+                                // third vector = the triangle's id
   std::vector<int32_t> tri_mat;
   raw_vector<int32_t> leaf_count;  // per node of the as-is array: leaves in its sub-tree (validate_chain, rt_trace.cuh)
   int n_nodes9 = 0, n_inner = 0, n_tris = 0;
