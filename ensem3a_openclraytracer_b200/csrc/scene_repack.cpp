@@ -3,6 +3,8 @@
 // right-first walk of the tree, which fixes every leaf's rank in the reference's visiting order (MathLib.cl:252-280).
 #include "scene_repack.h"
 
+#include <omp.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -62,8 +64,37 @@ bool quantise(const Axis &g, float mn, float mx, uint32_t *w_out) {
 
 }  // namespace
 
+namespace {
+
+// Host threads of the repack.  torchrun exports OMP_NUM_THREADS=1 to every rank "to avoid overload", which would build
+// the culling tree of every frame's upload on one core while the rest of the node idles: in that situation — one
+// thread allowed and a launcher that says how many ranks share the host — each rank takes its share of the cores
+// (at most 16).  B200RT_HOST_THREADS overrides; in every other case OpenMP's own setting stands.
+struct HostThreads {
+  int saved = 0;
+  HostThreads() {
+    int want = 0;
+    if (const char *q = getenv("B200RT_HOST_THREADS")) {
+      want = atoi(q);
+    } else if (omp_get_max_threads() == 1) {
+      const char *omp = getenv("OMP_NUM_THREADS"), *lws = getenv("LOCAL_WORLD_SIZE");
+      if (omp && lws && atoi(omp) == 1 && atoi(lws) >= 1) want = std::min(16, omp_get_num_procs() / atoi(lws));
+    }
+    if (want >= 1) {
+      saved = omp_get_max_threads();
+      omp_set_num_threads(want);
+    }
+  }
+  ~HostThreads() {
+    if (saved) omp_set_num_threads(saved);
+  }
+};
+
+}  // namespace
+
 int repack_scene(const float *vp, int64_t n_vp, const float *vn, int64_t n_vn, const int32_t *face, int64_t n_face,
                  int64_t n_materials, const float *bvh, int64_t n_bvh, Repacked *out, std::string *err, bool own_tree) {
+  HostThreads host_threads;
   Repacked &R = *out;
   const int n_nodes = (int)(n_bvh / 9), n_tris = (int)(n_face / 10);
   const int nvp = (int)(n_vp / 3), nvn = (int)(n_vn / 3), nm = (int)n_materials;

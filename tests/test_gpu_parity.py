@@ -336,6 +336,44 @@ def test_one_triangle_scene(gpu_ctx):
     assert np.array_equal(tri, prim["tri"]) and np.array_equal(bits(k), bits(prim["k"])) and (tri >= 0).any()
 
 
+def test_coincident_triangles_tie_goes_to_the_reference_first_visit(gpu_ctx):
+    """Every Cornell-box triangle twice, the copy with another material, both leaves under the leaf's old node: the two hits
+    are equal to the bit, the reference keeps the one it visits first (right child first, strict `k < H.k`,
+    MathLib.cl:263,275-280).  The fast traversal walks its own culling tree in its own order and must still report that
+    triangle (ranks), in the image as well as in the primary-hit ids."""
+    sc = fixtures.load_scene("cornell")
+    face = sc["faceData"].reshape(-1, 10)
+    n = len(face)
+    n_mat = sc["materialData"].size // 6
+    twin = face.copy()
+    twin[:, 0] = (twin[:, 0] + 1) % n_mat
+    bvh = sc["BVH"].reshape(-1, 9).copy()
+    extra = []
+    for i in range(len(bvh)):
+        t = int(bvh[i, 8])
+        if t == -1:
+            continue
+        a, b = len(bvh) + len(extra), len(bvh) + len(extra) + 1
+        extra.append(np.concatenate([[-1, -1], bvh[i, 2:8], [t]]))
+        extra.append(np.concatenate([[-1, -1], bvh[i, 2:8], [t + n]]))
+        bvh[i, 0], bvh[i, 1], bvh[i, 8] = a, b, -1
+    two = dict(sc, faceData=np.concatenate([face, twin]).reshape(-1).astype(np.int32),
+               BVH=np.concatenate([bvh, np.array(extra)]).astype(np.float32).reshape(-1), lightData=np.zeros(0, np.int32))
+    ibl = fixtures.load_ibl()
+    fixtures.upload(gpu_ctx, two, ibl)
+    res = 64
+    cam, env = fixtures.cam_env(sc["params"], res)
+    prim = oracle.primary(two, cam, res * res)
+    assert (prim["tri"] >= n).any()          # the right child is the twin: it wins the ties
+    for trav in TRAVERSALS:
+        want, cnt = oracle.render(two, cam, env, res * res, 4, 4, ibl)
+        out = gpu_ctx.render(cam, env, res, res, 4, 4, opts=rt.make_opts(traversal=trav))
+        assert np.array_equal(bits(out), bits(want)), trav
+        assert gpu_ctx.stats()["rays"] == cnt["rays"]
+    tri, k = gpu_ctx.primary_hits(cam, res, res)
+    assert np.array_equal(tri, prim["tri"]) and np.array_equal(bits(k), bits(prim["k"]))
+
+
 def test_nan_and_inf_semantics_survive(gpu_ctx):
     """inf * 0 -> NaN -> fmax(fmin(NaN,1),0) = 1 (white pixel) must come out as in the reference."""
     sc = fixtures.load_scene("cornell")

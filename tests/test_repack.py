@@ -157,6 +157,45 @@ def test_own_culling_tree_holds_every_triangle_once_inside_enclosing_boxes(name)
     assert deepest == info["cull_depth"]
 
 
+def coincident_scene(n):
+    """n copies of one triangle under a balanced hand-made tree: every leaf box and every centroid coincide (BVH.py itself
+    never terminates on such input, BVH.py:102-109 — but a caller may hand over any valid array)."""
+    vp = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0.5], np.float32)
+    vn = np.array([0, 0, 1], np.float32)
+    face = np.tile(np.array([0, 0, 0, 0, 0, 0, 0, 0, 1, 2], np.int32), n)
+    box = [0.0, 0.0, 0.0, 1.0, 1.0, 0.5]
+    nodes = []
+
+    def build(tris):
+        me = len(nodes)
+        nodes.append(None)
+        if len(tris) == 1:
+            nodes[me] = [-1, -1] + box + [tris[0]]
+        else:
+            l = build(tris[:len(tris) // 2])
+            r = build(tris[len(tris) // 2:])
+            nodes[me] = [l, r] + box + [-1]
+        return me
+
+    build(list(range(n)))
+    return dict(V_p=vp, V_n=vn, faceData=face, materialData=np.array([1, 1, 1, 1, 0.5, 1], np.float32),
+                BVH=np.array(nodes, np.float32).ravel())
+
+
+def test_own_culling_tree_on_coincident_triangles():
+    n = 1000
+    sc = coincident_scene(n)
+    nodes, info = probe(sc, own_tree=True)
+    assert info["canonical"] and info["n_inner"] == n - 1
+    refs = nodes[:, 6:8].astype(np.int64)
+    refs = np.where(refs >= 1 << 31, refs - (1 << 32), refs)
+    leaves = np.sort(~refs[refs < 0])
+    assert np.array_equal(leaves, np.arange(n))
+    assert info["cull_depth"] <= 12          # nothing to split by: halved by index, depth = ceil(log2 n) + 1 at most
+    pmin, pmax = decode(nodes, info)
+    assert (pmin <= np.array([0, 0, 0])).all() and (pmax >= np.array([1, 1, 0.5])).all()
+
+
 def renumber(bvh9):
     """the same tree with children numbered BELOW their parents (root stays 0): forces the general serial walk"""
     b = bvh9.reshape(-1, 9)
