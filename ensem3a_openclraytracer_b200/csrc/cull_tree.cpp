@@ -48,48 +48,53 @@ struct Box {
 struct Bins {
   Box box[3][kBins];
   int cnt[3][kBins];
-  void reset() {
+  void reset(int nb) {
     for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < kBins; ++b) { box[a][b].reset(); cnt[a][b] = 0; }
+      for (int b = 0; b < nb; ++b) { box[a][b].reset(); cnt[a][b] = 0; }
   }
-  void merge(const Bins &o) {
+  void merge(const Bins &o, int nb) {
     for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < kBins; ++b)
+      for (int b = 0; b < nb; ++b)
         if (o.cnt[a][b]) { box[a][b].grow(o.box[a][b]); cnt[a][b] += o.cnt[a][b]; }
   }
 };
 
+// The builder partitions the leaf boxes themselves, not indices into them: every pass over a range is then a sequential
+// sweep (with an index array the upper levels of a 5 M-triangle tree gather 160 MB at random, level after level).
+struct Prim {
+  float mn[3], mx[3];
+  int32_t id;
+  int32_t pad;
+};
+
 struct Builder {
-  const Repacked::f4 *tb;   // 2 per triangle: min.xyz, max.xyz of the leaf that holds it
-  int *idx;
+  Prim *prim;
   CullNode *nodes;
   std::atomic<int> next{0};
   std::atomic<int> depth{0};
 
-  const float *lo(int t) const { return &tb[2 * (size_t)t].x; }
-  const float *hi(int t) const { return &tb[2 * (size_t)t + 1].x; }
-  float centre(int t, int a) const { return 0.5f * lo(t)[a] + 0.5f * hi(t)[a]; }
+  static float centre(const Prim &p, int a) { return 0.5f * p.mn[a] + 0.5f * p.mx[a]; }
 
   int bins = 32;
-  int bin_of(float c, float c0, float scale) const {
+  static int bin_of(float c, float c0, float scale, int nb) {
     int b = (int)((c - c0) * scale);
-    return b < 0 ? 0 : (b >= bins ? bins - 1 : b);
+    return b < 0 ? 0 : (b >= nb ? nb - 1 : b);
   }
 
-  void bin_range(int begin, int end, const float *c0, const float *scale, Bins *out) const {
-    out->reset();
+  void bin_range(int begin, int end, const float *c0, const float *scale, int nb, Bins *out) const {
+    out->reset(nb);
     for (int i = begin; i < end; ++i) {
-      const int t = idx[i];
+      const Prim &p = prim[i];
       for (int a = 0; a < 3; ++a) {
         if (!(scale[a] > 0.0f)) continue;
-        const int b = bin_of(centre(t, a), c0[a], scale[a]);
-        out->box[a][b].grow(lo(t), hi(t));
+        const int b = bin_of(centre(p, a), c0[a], scale[a], nb);
+        out->box[a][b].grow(p.mn, p.mx);
         out->cnt[a][b]++;
       }
     }
   }
 
-  // builds the sub-tree over idx[begin, end) (end - begin >= 2); returns its interior index and box
+  // builds the sub-tree over prim[begin, end) (end - begin >= 2); returns its interior index and box
   int build(int begin, int end, int level, Box *box_out) {
     const int n = end - begin;
     const int me = next.fetch_add(1, std::memory_order_relaxed);
@@ -100,15 +105,17 @@ struct Builder {
       float c0[3] = {INFINITY, INFINITY, INFINITY}, c1[3] = {-INFINITY, -INFINITY, -INFINITY};
       for (int i = begin; i < end; ++i)
         for (int a = 0; a < 3; ++a) {
-          const float c = centre(idx[i], a);
+          const float c = centre(prim[i], a);
           c0[a] = std::min(c0[a], c);
           c1[a] = std::max(c1[a], c);
         }
+      // a range of a few triangles does not need (and should not pay for clearing and sweeping) all the bins
+      const int nb = std::min(bins, std::max(4, 2 * n));
       float scale[3];
       bool any = false;
       for (int a = 0; a < 3; ++a) {
         const float e = c1[a] - c0[a];
-        scale[a] = (e > 0.0f && std::isfinite(e)) ? (float)bins * (1.0f - 0x1p-20f) / e : 0.0f;
+        scale[a] = (e > 0.0f && std::isfinite(e)) ? (float)nb * (1.0f - 0x1p-20f) / e : 0.0f;
         if (!std::isfinite(scale[a])) scale[a] = 0.0f;
         any = any || scale[a] > 0.0f;
       }
@@ -120,14 +127,14 @@ struct Builder {
           for (int p = 0; p < kParts; ++p) {
             const int b0 = begin + (int)((long long)n * p / kParts), b1 = begin + (int)((long long)n * (p + 1) / kParts);
             Bins *dst = &part[p];
-#pragma omp task firstprivate(b0, b1, dst) shared(c0, scale)
-            bin_range(b0, b1, c0, scale, dst);
+#pragma omp task firstprivate(b0, b1, dst, nb) shared(c0, scale)
+            bin_range(b0, b1, c0, scale, nb, dst);
           }
 #pragma omp taskwait
-          B.reset();
-          for (int p = 0; p < kParts; ++p) B.merge(part[p]);
+          B.reset(nb);
+          for (int p = 0; p < kParts; ++p) B.merge(part[p], nb);
         } else {
-          bin_range(begin, end, c0, scale, &B);
+          bin_range(begin, end, c0, scale, nb, &B);
         }
         double best = INFINITY;
         int best_axis = -1, best_split = 0;
@@ -138,7 +145,7 @@ struct Builder {
           Box acc;
           acc.reset();
           int c = 0;
-          for (int b = bins - 1; b > 0; --b) {
+          for (int b = nb - 1; b > 0; --b) {
             if (B.cnt[a][b]) acc.grow(B.box[a][b]);
             c += B.cnt[a][b];
             right_area[b] = c ? acc.half_area() : 0.0;
@@ -146,7 +153,7 @@ struct Builder {
           }
           acc.reset();
           c = 0;
-          for (int b = 0; b < bins - 1; ++b) {   // split after bin b
+          for (int b = 0; b < nb - 1; ++b) {   // split after bin b
             if (B.cnt[a][b]) acc.grow(B.box[a][b]);
             c += B.cnt[a][b];
             if (c == 0 || right_cnt[b + 1] == 0) continue;
@@ -157,8 +164,8 @@ struct Builder {
         if (best_axis >= 0) {
           const int a = best_axis;
           const float a0 = c0[a], sc = scale[a];
-          int *m = std::partition(idx + begin, idx + end, [&](int t) { return bin_of(centre(t, a), a0, sc) <= best_split; });
-          mid = (int)(m - idx);
+          Prim *m = std::partition(prim + begin, prim + end, [&](const Prim &q) { return bin_of(centre(q, a), a0, sc, nb) <= best_split; });
+          mid = (int)(m - prim);
           if (mid == begin || mid == end) mid = begin + n / 2;   // cannot happen (both sides counted); keep the build total
         }
       }
@@ -167,8 +174,8 @@ struct Builder {
     int refl, refr;
     const bool spawn = n >= kTaskMin;
     if (mid - begin == 1) {
-      refl = ~idx[begin];
-      bl.reset(); bl.grow(lo(idx[begin]), hi(idx[begin]));
+      refl = ~prim[begin].id;
+      bl.reset(); bl.grow(prim[begin].mn, prim[begin].mx);
       if (level + 1 > depth.load(std::memory_order_relaxed)) bump_depth(level + 1);
     } else if (spawn) {
 #pragma omp task shared(refl, bl) firstprivate(begin, mid, level)
@@ -177,8 +184,8 @@ struct Builder {
       refl = build(begin, mid, level + 1, &bl);
     }
     if (end - mid == 1) {
-      refr = ~idx[mid];
-      br.reset(); br.grow(lo(idx[mid]), hi(idx[mid]));
+      refr = ~prim[mid].id;
+      br.reset(); br.grow(prim[mid].mn, prim[mid].mx);
       if (level + 1 > depth.load(std::memory_order_relaxed)) bump_depth(level + 1);
     } else {
       refr = build(mid, end, level + 1, &br);
@@ -214,12 +221,15 @@ void build_cull_tree(const Repacked::f4 *tboxes, int n_tris, std::vector<CullNod
   out->clear();
   *depth_out = 0;
   if (n_tris < 2) return;
-  std::vector<int> idx((size_t)n_tris);
-  for (int i = 0; i < n_tris; ++i) idx[i] = i;
+  std::vector<Prim> prim((size_t)n_tris);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n_tris; ++i) {
+    const Repacked::f4 &lo = tboxes[2 * (size_t)i], &hi = tboxes[2 * (size_t)i + 1];
+    prim[i] = Prim{{lo.x, lo.y, lo.z}, {hi.x, hi.y, hi.z}, i, 0};
+  }
   std::vector<CullNode> tmp((size_t)n_tris - 1);
   Builder B;
-  B.tb = tboxes;
-  B.idx = idx.data();
+  B.prim = prim.data();
   B.nodes = tmp.data();
   if (const char *q = getenv("B200RT_CULL_BINS")) {   // development knob
     const int v = atoi(q);
