@@ -240,9 +240,80 @@ void build_cull_tree(const Repacked::f4 *tboxes, int n_tris, std::vector<CullNod
 #pragma omp single
   B.build(0, n_tris, 0, &root);
   *depth_out = B.depth.load();
+  const int n_inner = n_tris - 1;
+
+  // ---- tree rotations: a child changes places with a grandchild on the other side where that shrinks the box in between
+  // (bottom-up sweeps until nothing improves; the root's box and every leaf box stay what they were)
+  int passes = n_tris > 1000000 ? 1 : 2;   // the sweeps are serial: one is most of the gain
+  if (const char *q = getenv("B200RT_CULL_ROTATE")) passes = atoi(q);   // development knob
+  if (passes > 0) {
+    auto area6 = [](const float *b) {
+      const double dx = (double)b[3] - b[0], dy = (double)b[4] - b[1], dz = (double)b[5] - b[2];
+      return dx * dy + dy * dz + dz * dx;
+    };
+    std::vector<int> post;
+    post.reserve((size_t)n_inner);
+    {
+      std::vector<int> st;
+      st.push_back(0);
+      while (!st.empty()) {     // reverse pre-order = children before parents
+        const int cur = st.back();
+        st.pop_back();
+        post.push_back(cur);
+        for (int k = 0; k < 2; ++k)
+          if (tmp[cur].ref[k] >= 0) st.push_back(tmp[cur].ref[k]);
+      }
+    }
+    for (int pass = 0; pass < passes; ++pass) {
+      long long changed = 0;
+      for (size_t q = post.size(); q-- > 0;) {
+        CullNode &N = tmp[post[q]];
+        double best_gain = 0.0;
+        int best_s = -1, best_g = -1;
+        float best_box[6];
+        for (int s = 0; s < 2; ++s) {
+          if (N.ref[s] < 0) continue;
+          const CullNode &X = tmp[N.ref[s]];
+          const float *y = N.box[1 - s];
+          const double ax = area6(N.box[s]);
+          for (int g = 0; g < 2; ++g) {       // the other side's child changes places with X's child g
+            const float *keep = X.box[1 - g];
+            float u[6];
+            for (int k = 0; k < 3; ++k) { u[k] = std::min(y[k], keep[k]); u[3 + k] = std::max(y[3 + k], keep[3 + k]); }
+            const double gain = ax - area6(u);
+            if (gain > best_gain) { best_gain = gain; best_s = s; best_g = g; memcpy(best_box, u, sizeof u); }
+          }
+        }
+        if (best_s < 0) continue;
+        CullNode &X = tmp[N.ref[best_s]];
+        const int y_ref = N.ref[1 - best_s];
+        float y_box[6];
+        memcpy(y_box, N.box[1 - best_s], sizeof y_box);
+        N.ref[1 - best_s] = X.ref[best_g];
+        memcpy(N.box[1 - best_s], X.box[best_g], sizeof y_box);
+        X.ref[best_g] = y_ref;
+        memcpy(X.box[best_g], y_box, sizeof y_box);
+        memcpy(N.box[best_s], best_box, sizeof best_box);
+        ++changed;
+      }
+      if (!changed) break;
+    }
+    // levels moved: the depth again
+    std::vector<std::pair<int, int>> st;
+    st.push_back({0, 0});
+    int deepest = 0;
+    while (!st.empty()) {
+      const auto cur = st.back();
+      st.pop_back();
+      for (int k = 0; k < 2; ++k) {
+        if (tmp[cur.first].ref[k] >= 0) st.push_back({tmp[cur.first].ref[k], cur.second + 1});
+        else deepest = std::max(deepest, cur.second + 1);
+      }
+    }
+    *depth_out = deepest;
+  }
 
   // final order: pre-order over sibling pairs
-  const int n_inner = n_tris - 1;
   std::vector<int> pos((size_t)n_inner, -1), order;
   order.reserve((size_t)n_inner);
   order.push_back(0);
