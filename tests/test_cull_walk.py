@@ -175,3 +175,28 @@ def test_walk_of_the_culling_tree_finds_the_reference_hit(name, n):
     assert (want_tri >= 0).sum() > len(rays) // 4
     # and it is the cheaper walk: fewer box tests than the reference's order over BVH.py's tree spends
     assert 2 * W.visits < cnt["box_tests"]
+
+
+@pytest.mark.parametrize("shift", [1.0e3, 1.0e5, 3.0e6])
+def test_scene_far_from_the_origin(shift):
+    """The Cornell box moved far away from the origin relative to its size: float32 spacing there is coarse (0.25 at 3e6),
+    the grid of the node records has to widen until its end planes enclose the root box after rounding, and the margin of
+    the conservative test grows with |coordinate| — the walk may visit more, it must not lose a hit."""
+    import ensem3a_openclraytracer_b200 as rt
+    sc = fixtures.load_scene("cornell")
+    vp = sc["V_p"].reshape(-1, 3).copy()
+    vp[:, 0] += f32(shift)
+    vp[:, 2] -= f32(shift / 3)
+    far = dict(sc, V_p=vp.reshape(-1).astype(f32))
+    far["BVH"] = rt.build_bvh(far["faceData"], far["V_p"])
+    far["params"] = dict(sc["params"], cam_x=str(float(sc["params"]["cam_x"]) + shift),
+                         cam_z=str(float(sc["params"]["cam_z"]) - shift / 3))
+    rays = rays_for(far, 1200, seed=3)
+    want_tri, want_k, _ = oracle.trace_rays(far, rays)
+    W = Walk(far)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for i, r in enumerate(rays):
+            t, k, ok = W.closest_hit(tuple(r[:3]), tuple(r[3:]))
+            if ok:
+                assert t == want_tri[i] and f32(k).view(np.uint32) == want_k[i].view(np.uint32), (shift, i)
+    assert (want_tri >= 0).sum() > 300
