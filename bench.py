@@ -494,7 +494,10 @@ def main():
         "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": public_config(cfg),
-        "impl_config": {"rng": "philox4x32-10 keyed (pixel,sample,bounce)", "traversal": "fast",
+        "impl_config": {"rng": "philox4x32-10 keyed (pixel,sample,bounce)",
+                        "traversal": "fast: conservative walk of a SAH culling tree built over the caller's leaf boxes "
+                                     "(csrc/cull_tree.cpp), exact Moeller-Trumbore on the leaves, winner validated with the "
+                                     "reference's exact leaf-box test",
                         "pipeline": "k_primary, then (spp*(maxBounce+2)) x (k_shade, k_trace) wavefront iterations",
                         "partition": "sample ranges" if world > 1 else "single GPU",
                         "sample_streams": streams_used,
