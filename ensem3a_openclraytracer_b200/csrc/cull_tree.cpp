@@ -24,7 +24,7 @@ namespace {
 
 constexpr int kBins = 64;             // capacity; the number in use is Builder::bins
 constexpr int kSahLevels = 64;        // below this level ranges are halved by index: bounds the depth at 64 + log2(n)
-constexpr int kTaskMin = 2048;        // sub-trees smaller than this are built by the task that reached them
+constexpr int kTaskMin = 256;         // sub-trees smaller than this are built by the task that reached them
 constexpr int kParallelBin = 1 << 18; // ranges larger than this are binned by several tasks
 
 struct Box {
